@@ -1,0 +1,39 @@
+// stream_kernels.cuh -- launch wrappers of the streaming engine (see stream_kernels.cu)
+#pragma once
+#include "common.cuh"
+
+namespace b2fwi {
+
+struct StepArgs {
+    int np, nr, nz, halo;
+    int64_t sp, sr;
+    float *out;            // slice written: u[t+1] (forward) or v[t-1] (backward)
+    const float *cur;      // u[t] / v[t]
+    const float *prev;     // u[t-1] / v[t+1]
+    const float *c1, *c2;  // update coefficients (b2fwi_prepare_coeffs)
+    // imaging condition (IMG != 0): grad += -u.dt2 * cur
+    float *grad;
+    const float *h0, *h1, *h2;  // IMG==1: u[t-1], u[t], u[t+1];  IMG==2: h1 = u.dt2[t]
+    float inv_dt2;
+    // forward extras (nullable)
+    float *illum;          // += cur^2
+    float *d2u;            // = (prev - 2 cur + out) / dt^2
+    // Laplacian weights pre-divided by h^2 for the plane / row / z directions
+    float c0;
+    float cp[B2FWI_MAX_R + 1], cr[B2FWI_MAX_R + 1], cz[B2FWI_MAX_R + 1];
+    int chunk;             // planes per CTA along the streamed axis (3-D); <= 0: pick automatically
+};
+
+void fill_stencil_weights(const Layout &L, StepArgs *a);
+int pick_chunk(const Layout &L);
+int launch_step(const Layout &L, StepArgs a, int img, cudaStream_t st);
+int launch_inject(float *field, const float *vp, float dt, const float *vals, const b2fwi_sparse *m,
+                  float *d2u, const float *cur, const float *prev, float inv_dt2, cudaStream_t st);
+int launch_interp(const float *field, float *out, const b2fwi_sparse *m, cudaStream_t st);
+int launch_coeffs(const Layout &L, const float *vp, const float *damp, float dt, float *coef, cudaStream_t st);
+int launch_accum_sq(const Layout &L, float *acc, const float *f, cudaStream_t st);
+int launch_geometry_mask(const b2fwi_grid *g, int nbl, const double *pts, int npts, double *mask, cudaStream_t st);
+int launch_crop_mask_acc(const b2fwi_grid *g, const Layout &L, int nbl, const float *field, const double *mask,
+                         double *out, cudaStream_t st);
+
+}  // namespace b2fwi

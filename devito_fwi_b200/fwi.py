@@ -1,0 +1,248 @@
+"""FWI objective ``(f, g)`` on the B200 propagator (API of the reference's fwi.py).
+
+Same functions, arguments and return values as the reference so that ``minimize.py``, ``optimize/``
+and ``misfit/`` run unchanged on top (fwi.py:59-81 fm_single/fm_multi, :104-129
+fix_source_illumination, :131-173 fwi_obj_single, :175-205 fwi_obj_multi, :236-246 fwi_loss).
+What moved: the per-shot host work (crop, 1+nrec Gaussian masks, the sum of u^2 over the whole
+history) runs on the device; the illumination is accumulated by the forward kernel itself; and the
+shot loop is partitioned over ranks with one all-reduce of [grad | illum | fval] (dist.py).
+The misfit stays a host plug-in ``misfit_func(syn, obs) -> (fval, adjoint_source)`` on numpy arrays.
+"""
+import ctypes
+from copy import deepcopy
+
+import numpy as np
+from scipy import interpolate
+
+from . import _lib, dist
+from .grid import Function, TimeFunction
+from .source import Receiver
+from .geometry import AcquisitionGeometry
+from .wavesolver import AcousticWaveSolver, grid_struct, _ptr, _stream
+
+__all__ = ['fm_single', 'fm_multi', 'fwi_obj_single', 'fwi_obj_multi', 'fwi_loss',
+           'fix_source_illumination', 'resample', 'Filter', 'least_square']
+
+
+def least_square(x, y):
+    """0.5*||x - y||^2 and its derivative (misfit/misfit.py:5-9)."""
+    r = x - y
+    return .5 * np.linalg.norm(r.flatten())**2, r
+
+
+class Filter(object):
+    """Butterworth band/low/high-pass applied to the source wavelet (fwi.py:31-44), via scipy."""
+
+    def __init__(self, filter_type, freqmin=None, freqmax=None, df=None, corners=10,
+                 zerophase=False, axis=-1):
+        assert filter_type.lower() in ['bandpass', 'lowpass', 'highpass']
+        self.filter_type = filter_type
+        self.freqmin, self.freqmax, self.df = freqmin, freqmax, df
+        self.corners, self.zerophase, self.axis = corners, zerophase, axis
+
+    def __call__(self, data):
+        from scipy.signal import iirfilter, sosfilt, zpk2sos
+        fe = 0.5 * self.df
+        if self.filter_type == 'bandpass':
+            if not (self.freqmin and self.freqmax and self.df):
+                raise ValueError
+            wn, btype = [self.freqmin / fe, self.freqmax / fe], 'band'
+        elif self.filter_type == 'lowpass':
+            if not (self.freqmax and self.df):
+                raise ValueError
+            wn, btype = self.freqmax / fe, 'lowpass'
+        else:
+            if not (self.freqmin and self.df):
+                raise ValueError
+            wn, btype = self.freqmin / fe, 'highpass'
+        z, p, k = iirfilter(self.corners, wn, btype=btype, ftype='butter', output='zpk')
+        sos = zpk2sos(z, p, k)
+        out = sosfilt(sos, data, axis=self.axis)
+        if self.zerophase:
+            out = np.flip(sosfilt(sos, np.flip(out, self.axis), axis=self.axis), self.axis)
+        return out
+
+
+def resample(x, t, t0, order=3):
+    """Cubic-spline resampling of traces from axis t0 to axis t; identity for equal steps (fwi.py:47-57)."""
+    if np.isclose(t[1] - t[0], t0[1] - t0[0]):
+        return x
+    out = np.zeros((t.size, x.shape[1]), dtype=np.float32)
+    for i in range(x.shape[1]):
+        out[:, i] = interpolate.splev(t, interpolate.splrep(t0, x[:, i], k=order))
+    return out
+
+
+def _shot_geometry(geometry, i):
+    return AcquisitionGeometry(geometry.model, geometry.rec_positions, geometry.src_positions[i, :],
+                               geometry.t0, geometry.tn, f0=geometry.f0, src_type=geometry.src_type,
+                               filter=geometry._filter)
+
+
+def fm_single(geometry, save=False):
+    """Forward modelling of one shot: (Receiver, wavefield)   [fwi.py:59-65]."""
+    solver = AcousticWaveSolver(geometry.model, geometry, space_order=geometry.model.space_order,
+                                profile=False)
+    data, u = solver.forward(vp=geometry.model.vp, save=save)[0:2]
+    return data, u
+
+
+def fm_multi(geometry, save=False):
+    """Forward modelling of every shot of a survey: list of Receivers   [fwi.py:67-81]."""
+    return [fm_single(_shot_geometry(geometry, i), save)[0] for i in range(geometry.nsrc)]
+
+
+def fix_source_illumination(geometry, g):
+    """Host version of the source/receiver muting (fwi.py:104-129), axis swap included; the
+    objective functions use the device kernel b2fwi_geometry_mask instead."""
+    if geometry.src_positions.shape[0] > 1:
+        raise ValueError("Only single source valid.")
+    dx, dz = geometry.model.spacing
+    nx, nz = geometry.model.shape
+    if g.shape != (nx, nz):
+        raise ValueError("Shape does not match!")
+    xx, zz = np.meshgrid(np.arange(0, nz) * dz, np.arange(0, nx) * dx)
+    sigma = dx + dz
+    pts = np.concatenate([geometry.src_positions[:1], geometry.rec_positions], axis=0)
+    for c0, c1 in pts:
+        g = g * (1. - np.exp(-.5 * ((xx - c0)**2 + (zz - c1)**2) / (sigma**2)))
+    return g
+
+
+# ---------------------------------------------------------------------------------------------
+_WORKSPACE = {}
+
+
+def _saved_wavefield(model, nt, space_order):
+    """Re-used nt-slice history buffer: only slots 0 and 1 need zeroing (every other slot is
+    overwritten by the forward sweep), instead of a fresh zero-filled TimeFunction per shot."""
+    key = ('u', model.grid._key(), nt)
+    u = _WORKSPACE.get(key)
+    if u is None:
+        _WORKSPACE.clear()
+        u = _WORKSPACE[key] = TimeFunction(name='u', grid=model.grid, save=nt, time_order=2,
+                                           space_order=space_order)
+    else:
+        d = u._buf.dev(write=True)
+        d[0:2].zero_()
+    return u
+
+
+_MASKS = {}
+
+
+def _geometry_mask(geometry):
+    """Device fp64 mask prod_k(1 - G_k) of one shot geometry, cached by content."""
+    import torch
+    model = geometry.model
+    pts = np.ascontiguousarray(np.concatenate([geometry.src_positions[:1], geometry.rec_positions]),
+                               dtype=np.float64)
+    key = (model.grid._key(), model.nbl, pts.tobytes())
+    m = _MASKS.get(key)
+    if m is None:
+        if len(_MASKS) > 512:
+            _MASKS.clear()
+        g = grid_struct(model.grid, model.space_order)
+        pts_dev = torch.from_numpy(pts).cuda()
+        m = torch.empty(model.shape, dtype=torch.float64, device='cuda')
+        _lib.check(_lib.lib().b2fwi_geometry_mask(ctypes.byref(g), model.nbl, _ptr(pts_dev), pts.shape[0],
+                                                  _ptr(m), _stream()))
+        _MASKS[key] = m
+    return m
+
+
+def _crop_mask_acc(geometry, field_dev, mask, out):
+    model = geometry.model
+    g = grid_struct(model.grid, model.space_order)
+    _lib.check(_lib.lib().b2fwi_crop_mask_accumulate(ctypes.byref(g), model.nbl, _ptr(field_dev), _ptr(mask),
+                                                     _ptr(out), _stream()))
+
+
+def _fwi_obj_single_dev(geometry, obs, misfit_func, direct_wave, resample_dt, calc_grad, acc):
+    """One shot; accumulates the masked cropped gradient / illumination into ``acc`` (device fp64,
+    [2, nx, nz]) and returns (fval, residual ndarray)."""
+    if geometry.src_positions.shape[0] > 1:
+        raise ValueError("Only single source valid.")
+    model = geometry.model
+    solver = AcousticWaveSolver(model, geometry, space_order=model.space_order, profile=False)
+    illum = Function(name='illum', grid=model.grid) if calc_grad else None
+    wfd = _saved_wavefield(model, geometry.nt, model.space_order) if calc_grad else None
+    pred, wfd = solver.forward(vp=model.vp, save=calc_grad, u=wfd, illum=illum)[0:2]
+
+    dw = direct_wave
+    if resample_dt is None:
+        resample_dt = geometry.dt
+    else:
+        obs = deepcopy(obs).resample(resample_dt) if not np.isclose(resample_dt, obs.time_range.step) else obs
+        pred = pred.resample(resample_dt)
+        if direct_wave is not None:
+            dw = direct_wave if np.isclose(resample_dt, direct_wave.time_range.step) \
+                else deepcopy(direct_wave).resample(resample_dt)
+    syn_data = pred.data
+    obs_data = obs.data
+    if direct_wave is not None:
+        syn_data = syn_data - dw.data
+        obs_data = obs_data - dw.data
+    fval, residual_data = misfit_func(syn_data, obs_data)
+
+    residual = Receiver(name="rec", grid=model.grid, time_range=geometry.time_axis,
+                        coordinates=geometry.rec_positions)
+    residual.data[:] = resample(residual_data, geometry.time_axis.time_values, pred.time_values)[:]
+    if calc_grad:
+        grad = Function(name="grad", grid=model.grid)
+        solver.gradient(rec=residual, u=wfd, vp=model.vp, grad=grad)
+        mask = _geometry_mask(geometry)
+        _crop_mask_acc(geometry, grad._buf.dev(), mask, acc[0])
+        _crop_mask_acc(geometry, illum._buf.dev(), mask, acc[1])
+    return fval, residual.data
+
+
+def fwi_obj_single(geometry, obs, misfit_func, direct_wave=None, resample_dt=None, calc_grad=False):
+    """Objective and gradient of one shot: (fval, crop_grad, residual, illum)   [fwi.py:131-173]."""
+    import torch
+    acc = torch.zeros((2,) + tuple(geometry.model.shape), dtype=torch.float64, device='cuda')
+    fval, res = _fwi_obj_single_dev(geometry, obs, misfit_func, direct_wave, resample_dt, calc_grad, acc)
+    if not calc_grad:
+        return fval, None, res, None
+    host = acc.cpu().numpy()
+    return fval, host[0], res, host[1]
+
+
+def fwi_obj_multi(geometry, obs, misfit_func, direct_wave=None, mask=None, precond=True,
+                  calc_grad=False):
+    """Sum over shots: (fval, grad float64[nx*nz], residuals)   [fwi.py:175-205].
+
+    Under torch.distributed the shots are split round-robin over ranks and [grad | illum | fval] is
+    all-reduced once; every rank returns the same (fval, grad). ``residuals`` then holds the local
+    shots' residuals only (they are only ever dumped to disk, minimize.py:50-51)."""
+    import torch
+    model = geometry.model
+    n = int(np.prod(model.shape))
+    buf = torch.zeros(2 * n + 1, dtype=torch.float64, device='cuda')
+    acc = buf[:2 * n].view((2,) + tuple(model.shape))
+    fval = .0
+    residuals = []
+    for i in dist.local_shots(geometry.nsrc):
+        geom_i = _shot_geometry(geometry, i)
+        dw = direct_wave[i] if direct_wave is not None else None
+        fval_, res_ = _fwi_obj_single_dev(geom_i, obs[i], misfit_func, dw, geometry.dt, calc_grad, acc)
+        fval += fval_
+        residuals += [res_]
+    buf[2 * n] = float(fval)
+    dist.all_reduce_sum(buf)
+    host = buf.cpu().numpy()
+    fval = float(host[2 * n])
+    grad = host[:n].reshape(model.shape).copy()
+    if calc_grad:
+        if precond:
+            grad /= np.sqrt(host[n:2 * n].reshape(model.shape) + 1e-30)
+        if mask is not None:
+            grad *= mask
+    return fval, grad.reshape(-1).astype(np.float64), residuals
+
+
+def fwi_loss(x, geometry, obs, misfit_func, direct_wave=None, mask=None, precond=True, calc_grad=True):
+    """Objective in squared slowness x = 1/vp^2 (flattened): (fval, grad, residuals)   [fwi.py:236-246]."""
+    v = 1. / np.sqrt(x.reshape(geometry.model.shape))
+    geometry.model.update('vp', v.reshape(geometry.model.shape))
+    return fwi_obj_multi(geometry, obs, misfit_func, direct_wave, mask, precond, calc_grad)

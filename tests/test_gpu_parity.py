@@ -1,0 +1,252 @@
+"""GPU parity: the CUDA path (through the Python mirror -> C ABI -> sm_100a kernels) against the
+CPU oracle on the same inputs.  Tolerances are north_star's: relative L2 <= 1e-5 on receiver
+traces and <= 1e-4 on gradients, measured against the fp64 oracle (the arbiter);
+the distance to the fp32 oracle is printed for information."""
+import numpy as np
+import pytest
+
+from tests.util import ref_model, rel_l2
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+
+TOL_TRACE = 1e-5
+TOL_GRAD = 1e-4
+
+
+def _b():
+    import devito_fwi_b200 as b
+    return b
+
+
+def _small_2d(so, shape=(75, 67), nbl=12, nsrc=2, nrec=23, tn=260.):
+    b = _b()
+    rng = np.random.default_rng(7)
+    vp = 1.5 + rng.random(shape).astype(np.float32) * 0.0
+    vp[:, shape[1] // 2:] = 2.5
+    vp[shape[0] // 3: shape[0] // 2, 10:30] = 3.0
+    model = b.Model(origin=(0., 0.), spacing=(10., 12.), shape=shape, space_order=so, vp=vp, nbl=nbl,
+                    bcs="damp")
+    src = np.empty((nsrc, 2))
+    src[:, 0] = np.linspace(203.3, 431.7, nsrc)
+    src[:, 1] = 37.9
+    rec = np.empty((nrec, 2))
+    rec[:, 0] = np.linspace(11.1, 733.3, nrec)
+    rec[:, 1] = 52.4
+    rec[1] = rec[0] + 0.5            # two receivers sharing all four cells: deterministic injection order
+    geom = b.AcquisitionGeometry(model, rec, src, 0., tn, f0=0.015, src_type='Ricker')
+    return model, geom
+
+
+@pytest.mark.parametrize("so", [2, 4, 6, 8, 12, 16])
+def test_forward_and_gradient_2d_orders(so):
+    b = _b()
+    model, geom = _small_2d(so)
+    solver = b.AcousticWaveSolver(model, geom, space_order=so)
+    rec, u, summary = solver.forward(save=True)
+    assert summary.gpointss > 0
+    rm = ref_model(model)
+    nt, dt = geom.nt, float(geom.dt)
+    src_data = np.array(geom.src.data, dtype=np.float64)
+    d64, u64 = ref.forward(rm, geom.src_positions, geom.rec_positions, src_data, nt, dt, save=True,
+                           space_order=so)
+    e = rel_l2(rec.data, d64)
+    eu = rel_l2(u.data, u64)
+    print("so=%d traces rel-L2 vs fp64 oracle %.2e, wavefield %.2e" % (so, e, eu))
+    assert e <= TOL_TRACE and eu <= TOL_TRACE
+    assert np.all(rec.data[0] == 0) and np.all(rec.data[-1] == 0)     # rows 0 and nt-1 never written
+
+    # gradient from a synthetic residual (= the data itself), accumulated into a non-zero grad
+    grad = b.Function(name='grad', grid=model.grid)
+    grad.data[:] = 1.0
+    residual = b.Receiver(name='res', grid=model.grid, time_range=geom.time_axis,
+                          coordinates=geom.rec_positions)
+    residual.data[:] = rec.data
+    solver.gradient(rec=residual, u=u, grad=grad)
+    g64 = ref.gradient(rm, d64, geom.rec_positions, u64, nt, dt, space_order=so,
+                       grad=np.ones(rm.shape_pml))
+    eg = rel_l2(grad.data, g64)
+    print("so=%d gradient rel-L2 vs fp64 oracle %.2e" % (so, eg))
+    assert eg <= TOL_GRAD
+
+
+def test_adjoint_dot_product_2d():
+    """<F s, r> == <s, F^T r>: forward and adjoint are discrete adjoints."""
+    b = _b()
+    model, geom = _small_2d(8, nsrc=1)
+    solver = b.AcousticWaveSolver(model, geom, space_order=8)
+    src = geom.src
+    rec, _, _ = solver.forward(src=src)
+    srca, _, _ = solver.adjoint(rec=rec)
+    lhs = np.dot(np.float64(rec.data.ravel()), np.float64(rec.data.ravel()))
+    rhs = np.dot(np.float64(srca.data.ravel()), np.float64(src.data.ravel()))
+    print("dot-product test: %.10e vs %.10e" % (lhs, rhs))
+    assert abs(lhs - rhs) / abs(lhs) < 2e-5
+    # and against the oracle
+    rm = ref_model(model)
+    sa64, _ = ref.adjoint(rm, np.float64(rec.data), geom.rec_positions, geom.src_positions, geom.nt,
+                          float(geom.dt), space_order=8)
+    assert rel_l2(srca.data, sa64) <= TOL_TRACE
+
+
+def test_forward_initial_state_time_window_and_scalar_vp():
+    """u passed in is the initial state; time_m/time_M restrict the sweep; vp may be a float."""
+    b = _b()
+    model, geom = _small_2d(4, nsrc=1)
+    solver = b.AcousticWaveSolver(model, geom, space_order=4)
+    nt = geom.nt
+    rec_a, u_a, _ = solver.forward(vp=2.0)
+    # same run split in two windows on one ring buffer
+    u = b.TimeFunction(name='u', grid=model.grid, time_order=2, space_order=4)
+    rec_b = geom.rec
+    solver.forward(vp=2.0, u=u, rec=rec_b, time_M=nt // 2)
+    solver.forward(vp=2.0, u=u, rec=rec_b, time_m=nt // 2 + 1)
+    assert np.array_equal(rec_a.data, rec_b.data)
+    assert np.array_equal(u_a.data, u.data)
+    rm = ref_model(model)
+    d64, _ = ref.forward(rm, geom.src_positions, geom.rec_positions, np.float64(geom.src.data), nt,
+                         float(geom.dt), space_order=4, vp=np.full(rm.shape_pml, 2.0))
+    assert rel_l2(rec_a.data, d64) <= TOL_TRACE
+
+
+@pytest.mark.parametrize("so", [4, 8, 16])
+def test_forward_gradient_3d(so):
+    b = _b()
+    shape, nbl = (34, 29, 38), 9
+    vp = np.full(shape, 1.5, dtype=np.float32)
+    vp[..., 14:] = 2.2
+    vp[10:20, 8:18, 20:30] = 2.9
+    model = b.Model(origin=(0., 0., 0.), spacing=(10., 10., 10.), shape=shape, space_order=so, vp=vp,
+                    nbl=nbl, bcs="damp")
+    src = np.array([[163.3, 141.2, 23.7]])
+    rx, ry = np.meshgrid(np.linspace(12.5, 320.1, 9), np.linspace(8.2, 271.9, 7), indexing='ij')
+    rec = np.stack([rx.ravel(), ry.ravel(), np.full(rx.size, 41.3)], axis=1)
+    geom = b.AcquisitionGeometry(model, rec, src, 0., 150., f0=0.02, src_type='Ricker')
+    solver = b.AcousticWaveSolver(model, geom, space_order=so)
+    d, u, _ = solver.forward(save=True)
+    rm = ref_model(model)
+    nt, dt = geom.nt, float(geom.dt)
+    d64, u64 = ref.forward(rm, src, rec, np.float64(geom.src.data), nt, dt, save=True, space_order=so)
+    e = rel_l2(d.data, d64)
+    print("3-D so=%d traces rel-L2 %.2e" % (so, e))
+    assert e <= TOL_TRACE
+    assert rel_l2(u.data, u64) <= TOL_TRACE
+    residual = b.Receiver(name='res', grid=model.grid, time_range=geom.time_axis, coordinates=rec)
+    residual.data[:] = d.data
+    grad, _ = solver.gradient(rec=residual, u=u)
+    g64 = ref.gradient(rm, d64, rec, u64, nt, dt, space_order=so)
+    eg = rel_l2(grad.data, g64)
+    print("3-D so=%d gradient rel-L2 %.2e" % (so, eg))
+    assert eg <= TOL_GRAD
+    # checkpoint + recompute must reproduce the full-history gradient bit for bit
+    grad_c, _ = solver.gradient(rec=residual, u=None, checkpointing=True, segment=7)
+    assert np.array_equal(grad_c.data, grad.data)
+    grad_c2, _ = solver.gradient(rec=residual, u=None, checkpointing=True)
+    assert np.array_equal(grad_c2.data, grad.data)
+
+
+def test_circle_fwi_kat_on_gpu():
+    """The reference's own gradient KAT (seismic/inversion/fwi.py:13-121) through the product API."""
+    b = _b()
+    shape, spacing, origin = (101, 101), (10., 10.), (0., 0.)
+    model = b.demo_model('circle-isotropic', vp_circle=3.0, vp_background=2.5, origin=origin,
+                         shape=shape, spacing=spacing, nbl=40)
+    model0 = b.demo_model('circle-isotropic', vp_circle=2.5, vp_background=2.5, origin=origin,
+                          shape=shape, spacing=spacing, nbl=40, grid=model.grid)
+    assert model.grid == model0.grid
+    src_coordinates = np.empty((1, 2))
+    src_coordinates[0, :] = np.array(model.domain_size) * .5
+    src_coordinates[0, 0] = 20.
+    rec_coordinates = np.empty((101, 2))
+    rec_coordinates[:, 1] = np.linspace(0, model.domain_size[0], num=101)
+    rec_coordinates[:, 0] = 980.
+    geometry = b.AcquisitionGeometry(model, rec_coordinates, src_coordinates, 0., 1000., f0=0.010,
+                                     src_type='Ricker')
+    solver = b.AcousticWaveSolver(model, geometry, space_order=4)
+    source_locations = np.empty((9, 2), dtype=np.float32)
+    source_locations[:, 0] = 20.
+    source_locations[:, 1] = np.linspace(0., 1000, num=9)
+
+    def fwi_gradient(vp_in):
+        grad = b.Function(name="grad", grid=model.grid)
+        objective = 0.
+        for i in range(9):
+            kw = dict(grid=model.grid, time_range=geometry.time_axis, coordinates=geometry.rec_positions)
+            residual, d_obs, d_syn = (b.Receiver(name=n, **kw) for n in ('residual', 'd_obs', 'd_syn'))
+            solver.geometry.src_positions[0, :] = source_locations[i, :]
+            solver.forward(vp=model.vp, rec=d_obs)
+            _, u0, _ = solver.forward(vp=vp_in, save=True, rec=d_syn)
+            residual.data[:] = d_syn.data[:] - d_obs.data[:]
+            objective += .5 * b.norm(residual)**2
+            solver.jacobian_adjoint(rec=residual, u=u0, vp=vp_in, grad=grad)
+        return objective, grad
+
+    ff, update = fwi_gradient(model0.vp)
+    print(ff, b.mmin(update), b.mmax(update))
+    assert np.isclose(ff, 39113, atol=1e1, rtol=0)
+    assert np.isclose(b.mmin(update), -821, atol=1e1, rtol=0)
+    assert np.isclose(b.mmax(update), 2442, atol=1e1, rtol=0)
+
+
+def test_marmousi_shot_vs_oracle():
+    """One full-size Marmousi shot (380x186 padded, so=8, nt=1357): traces, gradient, objective."""
+    b = _b()
+    from devito_fwi_b200 import configs
+    g_true, g_init, _, _ = configs.marmousi()
+    i = 14
+    obs = b.fwi.fm_single(b.fwi._shot_geometry(g_true, i))[0]
+    geom = b.fwi._shot_geometry(g_init, i)
+    solver = b.AcousticWaveSolver(geom.model, geom, space_order=8)
+    syn, u, _ = solver.forward(save=True)
+    res = b.Receiver(name='res', grid=geom.model.grid, time_range=geom.time_axis,
+                     coordinates=geom.rec_positions)
+    res.data[:] = syn.data - obs.data
+    f = .5 * np.linalg.norm(np.float64(res.data).ravel())**2
+    grad, _ = solver.gradient(rec=res, u=u)
+
+    rm_true, rm_init = ref_model(g_true.model), ref_model(g_init.model)
+    nt, dt = geom.nt, float(geom.dt)
+    wav = np.float64(geom.src.data)
+    o64, _ = ref.forward(rm_true, geom.src_positions, geom.rec_positions, wav, nt, dt)
+    s64, u64 = ref.forward(rm_init, geom.src_positions, geom.rec_positions, wav, nt, dt, save=True)
+    r64 = s64 - o64
+    f64 = .5 * np.linalg.norm(r64.ravel())**2
+    g64 = ref.gradient(rm_init, r64, geom.rec_positions, u64, nt, dt)
+    # SURVEY Appendix C secondary pins for this very shot
+    assert np.isclose(f64, 791388.47, rtol=1e-6)
+    assert np.isclose(np.linalg.norm(s64.ravel()), 2825.7933, rtol=1e-6)
+    print("marmousi shot: traces %.2e  residual %.2e  grad %.2e  f %.2e" % (
+        rel_l2(syn.data, s64), rel_l2(res.data, r64), rel_l2(grad.data, g64), abs(f - f64) / f64))
+    assert rel_l2(syn.data, s64) <= TOL_TRACE
+    assert rel_l2(obs.data, o64) <= TOL_TRACE
+    # gradient driven by the SAME residual on both sides
+    res.data[:] = r64
+    grad2, _ = solver.gradient(rec=res, u=u)
+    assert rel_l2(grad2.data, g64) <= TOL_GRAD
+    assert abs(f - f64) / f64 <= 1e-4
+
+
+def test_fwi_obj_multi_vs_oracle():
+    """(f, g) of fwi.py on a reduced circle survey: device post-processing vs the numpy restatement."""
+    b = _b()
+    from devito_fwi_b200 import configs
+    g_true, g_init = configs.circle(space_order=6, nsrc=3)
+    obs = b.fwi.fm_multi(g_true)
+    mask = np.ones(g_init.model.shape, dtype=np.float32)
+    mask[:5] = 0
+    f, g, residuals = b.fwi.fwi_obj_multi(g_init, obs, b.fwi.least_square, None, mask, True, True)
+    assert g.dtype == np.float64 and g.shape == (201 * 201,) and len(residuals) == 3
+
+    rm_true, rm_init = ref_model(g_true.model), ref_model(g_init.model)
+    nt, dt = g_init.nt, float(g_init.dt)
+    wav = np.float64(g_init.src.data[:, :1])
+    obs64 = [ref.forward(rm_true, g_true.src_positions[i], g_true.rec_positions, wav, nt, dt)[0]
+             for i in range(3)]
+    f64, g64, _ = ref.fwi_obj_multi(rm_init, g_init.src_positions, g_init.rec_positions, wav, nt, dt,
+                                    obs64, mask=mask, precond=True, calc_grad=True)
+    print("fwi_obj_multi: f %.3e  g %.3e" % (abs(f - f64) / f64, rel_l2(g, g64)))
+    assert abs(f - f64) / f64 <= 1e-4
+    assert rel_l2(g, g64) <= TOL_GRAD
+    # forward-only evaluation (line search, minimize.py:67-68)
+    f2, g2, _ = b.fwi.fwi_obj_multi(g_init, obs, b.fwi.least_square, None, mask, True, False)
+    assert np.isclose(f2, f, rtol=1e-6) and not g2.any()

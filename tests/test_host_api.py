@@ -1,0 +1,109 @@
+"""Host-side mirror of the reference's object API (re-targeted from seismic/test_seismic_utils.py
+and the set-up code of the drivers). CPU only."""
+import numpy as np
+import pytest
+
+import devito_fwi_b200 as b
+from devito_fwi_b200 import configs
+from devito_fwi_b200.sparse import resolve
+from oracle import ref
+
+
+@pytest.mark.parametrize('nbl', [0, 10, 40])
+@pytest.mark.parametrize('shape', [(21, 21), (21, 21, 21)])
+def test_damp(nbl, shape):
+    """seismic/test_seismic_utils.py:12-36"""
+    dims = len(shape)
+    model = b.demo_model('constant-isotropic', nbl=nbl, shape=shape, spacing=tuple([10.] * dims))
+    center = tuple(s // 2 + nbl for s in shape)
+    if nbl == 0:
+        assert model.damp == 0
+        return
+    assert model.grid.shape == tuple(s + 2 * nbl for s in shape)
+    assert model.damp.data[center] == 0             # demo models are built with bcs="damp"
+    with pytest.warns(UserWarning):
+        model._initialize_bcs(bcs="mask")
+    assert model.damp.data[center] == 1
+    assert np.all(model.damp.data <= 1)
+    with pytest.warns(UserWarning):
+        model._initialize_bcs(bcs="damp")
+    assert model.damp.data[center] == 0
+    # against the oracle's restatement of initialize_damp
+    want = ref.init_damp(model.grid.shape, nbl, [10.] * dims)
+    assert np.array_equal(model.damp.data, want)
+
+
+def test_default_geoms():
+    """seismic/test_seismic_utils.py:39-97: dt override, shapes, resample, zero source."""
+    model = b.demo_model('constant-isotropic', shape=(21, 21), spacing=(10., 10.), dt=1.0)
+    assert model.critical_dt == 1.0
+    geometry = b.setup_geometry(model, 250.0)
+    nrec = 21
+    assert geometry.grid == model.grid
+    assert geometry.nrec == nrec and geometry.nsrc == 1
+    assert geometry.src_type == "Ricker"
+    assert geometry.rec.shape == (251, nrec)
+    assert np.isclose(np.linalg.norm(geometry.rec.data), 0)
+    assert geometry.src.shape == (251, 1)
+    assert geometry.new_src(src_type=None).data.max() == 0 and geometry.new_src(src_type=None).shape == (251, 1)
+    rec2 = geometry.rec.resample(num=501)
+    assert rec2.shape == (501, nrec)
+    assert np.isclose(rec2.time_range.step, 0.5)
+    assert geometry.src.resample(dt=1.0) is not None
+    with pytest.raises(ValueError):
+        b.demo_model('constant-isotropic', shape=(21, 21), spacing=(10., 10.), dt=100.0).critical_dt
+
+
+def test_model_update_and_cfl():
+    g_true, g_init, g_const, mask = configs.marmousi()
+    m = g_init.model
+    assert m.grid.shape == (380, 186) and m.critical_dt == 2.95 and g_init.nt == 1357
+    assert np.isclose(m._cfl_coeff, 0.5189321559)
+    assert mask.shape == (300, 106) and not mask[:, :7].any()
+    v = np.full(m.shape, 2.0, dtype=np.float32)
+    v[0, 0] = 1.7
+    m.update('vp', v)
+    assert m.vp.data.shape == (380, 186)
+    assert np.all(m.vp.data[:41, :41] == np.float32(1.7))       # edge replication into the corner
+    with pytest.raises(ValueError):
+        m.update('vp', np.zeros((3, 3), dtype=np.float32))
+    ga, gb = configs.marmousi2()[:2]
+    assert ga.model.grid.shape == (420, 220) and ga.nt == 1501 and ga.nrec == 340 and ga.nsrc == 31
+    ca, cb = configs.circle()
+    assert ca.model.grid.shape == (281, 281) and ca.nt == 1001 and ca.nsrc == 11 and ca.nrec == 201
+
+
+def test_ricker_and_time_axis_match_oracle():
+    g = configs.marmousi()[0]
+    nt, stop, tv = ref.time_axis(0., 4000., 2.95)
+    assert nt == g.nt
+    assert np.allclose(g.src.data[:, 0], ref.ricker(0.007, tv).astype(np.float32))
+    assert g.src.data.dtype == np.float32 and g.src.coordinates.data.dtype == np.float32
+
+
+def test_sparse_resolution_weights():
+    """Multilinear weights: partition of unity, exact at nodes, off-grid receivers."""
+    g = configs.marmousi()[0]
+    off, w = resolve(g.grid, g.rec_positions)
+    assert off.shape == (300, 4) and (off >= 0).all()
+    assert np.allclose(w.sum(axis=1), 1.0, atol=1e-6)
+    # depth 60 m is a grid line: the two z1 corners carry zero weight
+    assert np.allclose(w[:, 1], 0, atol=1e-7) and np.allclose(w[:, 3], 0, atol=1e-7)
+    pitch = g.grid.pitch
+    ix, iz = off[:, 0] // pitch, off[:, 0] % pitch
+    assert np.array_equal(iz, np.full(300, 42)) and ix[0] == 41
+    # outside the padded grid -> dropped corners
+    off2, _ = resolve(g.grid, np.array([[-1300., 60.], [1e6, 60.]]))
+    assert (off2 == -1).all()
+    # 3-D
+    grid3 = b.Grid(shape=(11, 12, 13), extent=(100., 110., 120.))
+    off3, w3 = resolve(grid3, np.array([[33.3, 47.1, 58.9]]))
+    assert off3.shape == (1, 8) and np.isclose(w3.sum(), 1.0, atol=1e-6)
+
+
+def test_shot_partition():
+    from devito_fwi_b200 import dist
+    shots = [dist.local_shots(29, r, 8) for r in range(8)]
+    assert sorted(sum(shots, [])) == list(range(29))
+    assert max(map(len, shots)) - min(map(len, shots)) <= 1
+    assert dist.local_shots(29) == list(range(29))
