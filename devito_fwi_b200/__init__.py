@@ -11,6 +11,6 @@ from .source import (TimeAxis, PointSource, Receiver, Shot, WaveletSource, Ricke
 from .geometry import AcquisitionGeometry, setup_geometry, setup_rec_coords  # noqa: F401
 from .preset_models import demo_model  # noqa: F401
 from .wavesolver import AcousticWaveSolver, PerformanceSummary  # noqa: F401
-from . import fwi, dist  # noqa: F401
+from . import fwi, dist, resident  # noqa: F401
 
 __version__ = "0.1.0"

@@ -38,7 +38,7 @@ struct Layout {
     int64_t base;        // offset of domain cell (0,0,0)
     int64_t elems;       // floats per haloed slice
     int R;               // stencil radius
-    float inv_h2[3];     // 1/h^2 for plane, row, z directions
+    double inv_h2[3];    // 1/h^2 for plane, row, z directions
 };
 
 int make_layout(const b2fwi_grid *g, Layout *L);

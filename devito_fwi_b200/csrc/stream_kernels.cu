@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(256, 2) step_kernel(const __grid_constant__ St
 
         if (active) {
             const float4 C = q[QC];
-            float lap[4] = {a.c0 * C.x, a.c0 * C.y, a.c0 * C.z, a.c0 * C.w};
+            float lap[4] = {fmaf(a.c0, C.x, a.c0_lo * C.x), fmaf(a.c0, C.y, a.c0_lo * C.y),
+                            fmaf(a.c0, C.z, a.c0_lo * C.z), fmaf(a.c0, C.w, a.c0_lo * C.w)};
             if (NDIM == 3) {
 #pragma unroll
                 for (int k = 1; k <= R; k++) {

@@ -19,7 +19,7 @@ struct StepArgs {
     float *illum;          // += cur^2
     float *d2u;            // = (prev - 2 cur + out) / dt^2
     // Laplacian weights pre-divided by h^2 for the plane / row / z directions
-    float c0;
+    float c0, c0_lo;       // centre weight as hi + lo: exactly -2*sum of the rounded side weights (see api.cu)
     float cp[B2FWI_MAX_R + 1], cr[B2FWI_MAX_R + 1], cz[B2FWI_MAX_R + 1];
     int chunk;             // planes per CTA along the streamed axis (3-D); <= 0: pick automatically
 };

@@ -88,8 +88,19 @@ def fm_single(geometry, save=False):
 
 
 def fm_multi(geometry, save=False):
-    """Forward modelling of every shot of a survey: list of Receivers   [fwi.py:67-81]."""
-    return [fm_single(_shot_geometry(geometry, i), save)[0] for i in range(geometry.nsrc)]
+    """Forward modelling of every shot of a survey: list of Receivers   [fwi.py:67-81].
+    2-D surveys run as one batched launch of the SM-resident engine (all shots concurrently)."""
+    survey = _resident_survey(geometry, list(range(geometry.nsrc))) if not save else None
+    if survey is None:
+        return [fm_single(_shot_geometry(geometry, i), save)[0] for i in range(geometry.nsrc)]
+    rec = survey.forward(save=False).clone()
+    shots = []
+    for k in range(geometry.nsrc):
+        r = Receiver(name='rec', grid=geometry.grid, time_range=geometry.time_axis,
+                     coordinates=geometry.rec_positions)
+        r._sdata.adopt_dev(rec[k])
+        shots.append(r)
+    return shots
 
 
 def fix_source_illumination(geometry, g):
@@ -197,6 +208,114 @@ def _fwi_obj_single_dev(geometry, obs, misfit_func, direct_wave, resample_dt, ca
     return fval, residual.data
 
 
+_SURVEYS = {}
+ENGINE = 'auto'     # 'auto' | 'stream' (force the per-shot streaming engine; used by the parity tests)
+
+
+def _resident_survey(geometry, shots):
+    """Cached ResidentSurvey for (geometry, shots), or None when the SM-resident engine does not apply."""
+    from .resident import ResidentSurvey
+    if ENGINE == 'stream' or not shots or not ResidentSurvey.supported(geometry):
+        return None
+    model = geometry.model
+    key = (id(model), model.grid._key(), model.space_order, tuple(shots), float(geometry.dt), geometry.nt,
+           geometry.src_positions.tobytes(), geometry.rec_positions.tobytes(), geometry.f0, geometry.src_type,
+           id(geometry._filter))
+    sv = _SURVEYS.get(key)
+    if sv is None:
+        if len(_SURVEYS) >= 4:
+            _SURVEYS.clear()
+        try:
+            sv = ResidentSurvey(geometry, shots)
+        except ValueError:
+            return None
+        _SURVEYS[key] = sv
+    return sv
+
+
+class LazyResidual(object):
+    """Residual of one shot living on the device; converts to numpy on first host use
+    (minimize.py only dumps residuals every few iterations, minimize.py:50-51,146-152)."""
+
+    def __init__(self, tensor):
+        self._t = tensor
+        self._h = None
+        self.shape = tuple(tensor.shape)
+        self.dtype = np.dtype(np.float32)
+
+    def __array__(self, dtype=None, copy=None):
+        if self._h is None:
+            self._h = self._t.cpu().numpy()
+        return self._h if dtype is None else self._h.astype(dtype)
+
+    def astype(self, dtype):
+        return np.asarray(self).astype(dtype)
+
+    def __getitem__(self, idx):
+        return np.asarray(self)[idx]
+
+
+def _is_l2(misfit_func):
+    return misfit_func is least_square or getattr(misfit_func, '__name__', '') == 'least_square'
+
+
+def _stack_dev(receivers, shots, cache_owner, tag):
+    """[nshots, nt, nrec] device tensor of a list of Receivers; re-used while the SAME list object is
+    passed again (a new list - e.g. fresh host data every call - is uploaded again)."""
+    import torch
+    cache = cache_owner.__dict__.setdefault('_dev_stacks', {})
+    hit = cache.get(tag)
+    if hit is not None and hit[0] is receivers and hit[1] == tuple(shots):
+        return hit[2]
+    t = torch.stack([receivers[i]._sdata.dev() for i in shots]).contiguous()
+    cache[tag] = (receivers, tuple(shots), t)
+    return t
+
+
+def _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_grad, acc):
+    """Shots of ``survey`` in two launches (forward, backward); returns (fval, residual list)."""
+    import torch
+    lib = _lib.lib()
+    shots = survey.shots
+    syn = survey.forward(save=calc_grad, illum=calc_grad)
+    if _is_l2(misfit_func):
+        # on-device least squares (misfit/misfit.py:5-9) incl. direct-wave subtraction (fwi.py:146-150)
+        obs_d = _stack_dev(obs, shots, survey, 'obs')
+        dw_d = _stack_dev(direct_wave, shots, survey, 'dw') if direct_wave is not None else None
+        if getattr(survey, '_res', None) is None:
+            survey._res = torch.empty_like(syn)
+            survey._fval = torch.zeros(1, dtype=torch.float64, device='cuda')
+            survey._scratch = torch.empty(1024, dtype=torch.float64, device='cuda')
+        survey._fval.zero_()
+        _lib.check(lib.b2fwi_l2_misfit(_ptr(syn), _ptr(obs_d), _ptr(dw_d), syn.numel(), _ptr(survey._res),
+                                       _ptr(survey._fval), _ptr(survey._scratch), _stream()))
+        residual = survey._res
+        fval = survey._fval            # stays on the device until the all-reduce
+        residuals = [LazyResidual(residual[k]) for k in range(len(shots))]
+    else:
+        # host plug-in misfit: misfit_func(syn, obs) -> (fval, adjoint_source) on numpy arrays
+        syn_h = syn.cpu().numpy()
+        res_h = np.empty_like(syn_h)
+        fval = 0.
+        for k, i in enumerate(shots):
+            syn_data, obs_data = syn_h[k], obs[i].data
+            if direct_wave is not None:
+                syn_data = syn_data - direct_wave[i].data
+                obs_data = obs_data - direct_wave[i].data
+            f_, r_ = misfit_func(syn_data, obs_data)
+            fval += f_
+            res_h[k] = r_
+        residual = torch.from_numpy(res_h).cuda()
+        residuals = [res_h[k] for k in range(len(shots))]
+    if calc_grad:
+        grad = survey.gradient(residual)
+        for k, i in enumerate(shots):
+            mask = _geometry_mask(_shot_geometry(geometry, i))
+            survey.window_mask_accumulate(grad[k], mask, acc[0])
+            survey.window_mask_accumulate(survey.illum[k], mask, acc[1])
+    return fval, residuals
+
+
 def fwi_obj_single(geometry, obs, misfit_func, direct_wave=None, resample_dt=None, calc_grad=False):
     """Objective and gradient of one shot: (fval, crop_grad, residual, illum)   [fwi.py:131-173]."""
     import torch
@@ -222,13 +341,22 @@ def fwi_obj_multi(geometry, obs, misfit_func, direct_wave=None, mask=None, preco
     acc = buf[:2 * n].view((2,) + tuple(model.shape))
     fval = .0
     residuals = []
-    for i in dist.local_shots(geometry.nsrc):
-        geom_i = _shot_geometry(geometry, i)
-        dw = direct_wave[i] if direct_wave is not None else None
-        fval_, res_ = _fwi_obj_single_dev(geom_i, obs[i], misfit_func, dw, geometry.dt, calc_grad, acc)
-        fval += fval_
-        residuals += [res_]
-    buf[2 * n] = float(fval)
+    shots = dist.local_shots(geometry.nsrc)
+    same_dt = all(np.isclose(geometry.dt, obs[i].time_range.step) for i in shots)
+    survey = _resident_survey(geometry, shots) if same_dt else None
+    if survey is not None:
+        fval, residuals = _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_grad, acc)
+    else:
+        for i in shots:
+            geom_i = _shot_geometry(geometry, i)
+            dw = direct_wave[i] if direct_wave is not None else None
+            fval_, res_ = _fwi_obj_single_dev(geom_i, obs[i], misfit_func, dw, geometry.dt, calc_grad, acc)
+            fval += fval_
+            residuals += [res_]
+    if hasattr(fval, 'is_cuda'):
+        buf[2 * n:2 * n + 1].copy_(fval)
+    else:
+        buf[2 * n] = float(fval)
     dist.all_reduce_sum(buf)
     host = buf.cpu().numpy()
     fval = float(host[2 * n])

@@ -41,6 +41,7 @@ def initialize_damp(damp, padsizes, spacing, abc_type="damp", fs=False):
     ``"mask"`` starts from 1 and subtracts instead."""
     sign = -1.0 if abc_type == "mask" else 1.0
     field = np.full(damp.grid.shape, 1.0 if abc_type == "mask" else 0.0, dtype=np.float64)
+    profiles = []
     for d, ((nbl, nbr), h) in enumerate(zip(padsizes, spacing)):
         n = damp.grid.shape[d]
         prof = np.zeros(n)
@@ -55,7 +56,10 @@ def initialize_damp(damp, padsizes, spacing, abc_type="damp", fs=False):
             else:
                 prof[n - width:] += val[::-1]
         field += prof.reshape([n if k == d else 1 for k in range(damp.grid.dim)])
+        profiles.append(prof)
     damp.data[...] = field.astype(damp.dtype)
+    # the profile is separable (a sum of 1-D profiles); the SM-resident engine uses that
+    damp._profiles = profiles if abc_type == "damp" else None
 
 
 def _second_derivative_weights(half_width):

@@ -1,0 +1,276 @@
+"""Host side of the SM-resident 2-D engine (csrc/resident2d.cu): decomposition plan, injection /
+recording maps, device buffers of one survey, and the batched forward / gradient calls.
+
+``ResidentSurvey`` is what the shot loops of fwi.py (fm_multi fwi.py:67-81, fwi_obj_multi
+fwi.py:183-199) run on: all shots of the rank go through ONE kernel launch per sweep, one
+thread-block cluster per shot.  It needs a 2-D model, space_order 4/6/8, the separable damping
+profile of seismic/model.py:31-49 and a zero initial wavefield; otherwise callers fall back to
+the per-shot streaming engine (``ResidentSurvey.supported`` tells).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .grid import Function, HALO
+from .sparse import resolve
+from .wavesolver import grid_struct, _ptr, _stream
+
+__all__ = ['ResidentSurvey', 'plan_model']
+
+MAX_CELLS = 1024      # RES2D_MAX_CELLS
+
+
+class Plan(ctypes.Structure):
+    """struct b2fwi_res2d_plan"""
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ('cluster', 'rows_per_thread', 'groups', 'threads', 'rows_cta', 'tile_rows', 'smem_bytes',
+                 'wx0', 'wx1', 'wq0', 'wq1')]
+
+
+class Maps(ctypes.Structure):
+    """struct b2fwi_res2d_maps (device pointers)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ('inj_desc', 'inj_cptr', 'inj_pt', 'inj_w', 'thr_mask', 'thr_base',
+                 'itp_desc', 'itp_pt', 'itp_off', 'itp_w')]
+
+
+def plan_model(grid, space_order, nbl, min_cluster=1):
+    """b2fwi_res2d_plan_model; returns a Plan or None when the grid does not fit the engine."""
+    if grid.dim != 2 or space_order not in (4, 6, 8):
+        return None
+    g = grid_struct(grid, space_order)
+    plan = Plan()
+    rc = _lib.lib().b2fwi_res2d_plan_model(ctypes.byref(g), int(nbl), int(min_cluster), ctypes.byref(plan))
+    return plan if rc == 0 else None
+
+
+def build_maps(grid, plan, R, inj_coords, itp_coords=None):
+    """numpy arrays of struct b2fwi_res2d_maps for a list of shots.
+
+    inj_coords: per shot, [npoint, 2] positions injected into the field (source(s) on the forward
+    sweep, receivers on the backward sweep).  itp_coords: per shot, receiver positions recorded by
+    the forward sweep (or None).  Cells hit by several points gather their contributions in
+    ascending point order, exactly like sparse.SparseMap."""
+    C, P, T = plan.cluster, plan.rows_per_thread, plan.threads
+    rows_cta = plan.rows_cta
+    nzq = (grid.shape[1] + 3) // 4
+    gpitch = grid.pitch
+    spitch = nzq * 4
+    nshots = len(inj_coords)
+    inj_desc = np.zeros((nshots * C, 2), dtype=np.int32)
+    thr_mask = np.zeros((nshots * C, T), dtype=np.uint64)
+    thr_base = np.zeros((nshots * C, T), dtype=np.int32)
+    cptr_all, pt_all, w_all = [], [], []
+    ncontrib = 0
+    cell_base = 0
+    for s in range(nshots):
+        off, w = resolve(grid, inj_coords[s])
+        npoint, nc = off.shape
+        flat_off, flat_w = off.ravel(), w.ravel()
+        pt = np.repeat(np.arange(npoint, dtype=np.int32), nc)
+        valid = flat_off >= 0
+        v_off, v_w, v_pt = flat_off[valid], flat_w[valid], pt[valid]
+        row, col = np.divmod(v_off - 0, gpitch)
+        crank = row // rows_cta
+        lr = row - crank * rows_cta
+        tid = (lr // P) * nzq + col // 4
+        bit = (lr % P) * 4 + col % 4
+        order = np.lexsort((v_pt, bit, tid, crank))            # CTA, owner thread, bit, then point order
+        crank, tid, bit, v_w, v_pt = crank[order], tid[order], bit[order], v_w[order], v_pt[order]
+        key = (crank.astype(np.int64) * T + tid) * 64 + bit
+        for c in range(C):
+            sel = crank == c
+            sc = s * C + c
+            k = key[sel]
+            cells, start = np.unique(k, return_index=True)
+            ncell = cells.size
+            if ncell > MAX_CELLS:
+                return None
+            inj_desc[sc] = (ncell, cell_base)
+            cptr = np.concatenate([start, [k.size]]).astype(np.int32) + ncontrib
+            cptr_all.append(cptr)
+            pt_all.append(v_pt[sel])
+            w_all.append(v_w[sel])
+            ncontrib += int(k.size)
+            cell_base += ncell + 1
+            ctid = ((cells // 64) % T).astype(np.int64)
+            cbit = (cells % 64).astype(np.uint64)
+            np.bitwise_or.at(thr_mask[sc], ctid, np.uint64(1) << cbit)
+            first = np.full(T, -1, dtype=np.int64)
+            # cells are sorted by (tid, bit): the first occurrence of a tid is its base slot
+            utid, ufirst = np.unique(ctid, return_index=True)
+            first[utid] = ufirst
+            thr_base[sc] = np.where(first >= 0, first, 0)
+    maps = dict(inj_desc=inj_desc, inj_cptr=np.concatenate(cptr_all).astype(np.int32),
+                inj_pt=np.concatenate(pt_all).astype(np.int32) if pt_all else np.zeros(1, np.int32),
+                inj_w=np.concatenate(w_all).astype(np.float32) if w_all else np.zeros(1, np.float32),
+                thr_mask=thr_mask, thr_base=thr_base)
+    if maps['inj_pt'].size == 0:
+        maps['inj_pt'] = np.zeros(1, np.int32)
+        maps['inj_w'] = np.zeros(1, np.float32)
+
+    itp_desc = np.zeros((nshots * C, 2), dtype=np.int32)
+    ipt, ioff, iw = [], [], []
+    base = 0
+    if itp_coords is not None:
+        nx = grid.shape[0]
+        for s in range(nshots):
+            off, w = resolve(grid, itp_coords[s])
+            npoint = off.shape[0]
+            row, col = np.divmod(np.where(off >= 0, off, 0), gpitch)
+            # owner: the CTA holding the point's base row (corner 0); out-of-grid points go to an end CTA
+            coords = np.ascontiguousarray(np.reshape(itp_coords[s], (-1, 2)), dtype=np.float32)
+            ix = np.floor((coords[:, 0] - np.float32(grid.origin[0])) / np.float32(grid.spacing[0])).astype(np.int64)
+            owner = np.clip(ix, 0, nx - 1) // rows_cta
+            for c in range(C):
+                sel = np.nonzero(owner == c)[0]
+                sc = s * C + c
+                itp_desc[sc] = (sel.size, base)
+                trow = row[sel] - c * rows_cta + R
+                ok = (off[sel] >= 0) & (trow >= 0) & (trow < plan.tile_rows)
+                ioff.append(np.where(ok, trow * spitch + col[sel], -1).astype(np.int32))
+                iw.append(w[sel].astype(np.float32))
+                ipt.append(sel.astype(np.int32))
+                base += sel.size
+    maps.update(itp_desc=itp_desc,
+                itp_pt=np.concatenate(ipt) if base else np.zeros(1, np.int32),
+                itp_off=np.concatenate(ioff) if base else np.full((1, 4), -1, np.int32),
+                itp_w=np.concatenate(iw) if base else np.zeros((1, 4), np.float32))
+    return maps
+
+
+class _DevMaps(object):
+    def __init__(self, maps):
+        import torch
+        self.t = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.int64) if v.dtype == np.uint64
+                                      else np.ascontiguousarray(v)).cuda() for k, v in maps.items()}
+        self.struct = Maps()
+        for k, t in self.t.items():
+            setattr(self.struct, k, t.data_ptr())
+
+    def byref(self):
+        return ctypes.byref(self.struct)
+
+
+class ResidentSurvey(object):
+    """Device-resident state of the shots ``shots`` of ``geometry`` (default: all of them)."""
+
+    def __init__(self, geometry, shots=None, space_order=None, min_cluster=1):
+        import torch
+        self.geometry = geometry
+        model = self.model = geometry.model
+        self.grid = model.grid
+        self.space_order = int(space_order or model.space_order)
+        self.R = self.space_order // 2
+        self.shots = list(range(geometry.nsrc)) if shots is None else list(shots)
+        self.nshots = len(self.shots)
+        self.plan = plan_model(self.grid, self.space_order, model.nbl, min_cluster)
+        if self.plan is None or not self.supported(geometry, self.space_order):
+            raise ValueError("model does not fit the SM-resident engine")
+        self.nt = geometry.nt
+        self.dt = float(geometry.dt)
+        self.nrec = geometry.nrec
+        self.gs = grid_struct(self.grid, self.space_order)
+        p = self.plan
+        self.wshape = (p.wx1 - p.wx0, (p.wq1 - p.wq0) * 4)
+        self.col0 = model.nbl - p.wq0 * 4
+        # damping profiles (damp/dt), separable
+        model._initialize_bcs(bcs="damp")
+        px, pz = model.damp._profiles
+        nzq4 = 4 * ((self.grid.shape[1] + 3) // 4)
+        sz = np.zeros(nzq4, dtype=np.float32)
+        sz[:pz.size] = pz / self.dt
+        self.sx = torch.from_numpy((px / self.dt).astype(np.float32)).cuda()
+        self.sz = torch.from_numpy(sz).cuda()
+        # source wavelets [nshots][nt][1] and maps
+        wav = np.asarray(geometry.src.data, dtype=np.float32)          # [nt, nsrc_total]
+        self.src = torch.from_numpy(np.ascontiguousarray(wav[:, self.shots].T[:, :, None])).cuda()
+        src_pos = [geometry.src_positions[i:i + 1] for i in self.shots]
+        rec_pos = [geometry.rec_positions] * self.nshots
+        mf = build_maps(self.grid, p, self.R, src_pos, rec_pos)
+        mb = build_maps(self.grid, p, self.R, rec_pos, None)
+        if mf is None or mb is None:
+            raise ValueError("too many injection cells per CTA for the SM-resident engine")
+        self.maps_fwd, self.maps_bwd = _DevMaps(mf), _DevMaps(mb)
+        self.B = torch.zeros(self.grid.slice_shape, dtype=torch.float32, device='cuda')
+        self.rec = torch.zeros((self.nshots, self.nt, self.nrec), dtype=torch.float32, device='cuda')
+        self.hist = None
+        self.illum = None
+        self.grad = None
+
+    @staticmethod
+    def supported(geometry, space_order=None):
+        model = geometry.model
+        so = int(space_order or model.space_order)
+        if model.dim != 2 or so not in (4, 6, 8) or np.dtype(model.dtype) != np.float32 or model.nbl == 0:
+            return False
+        if not isinstance(model.vp, Function) or HALO != 0:
+            return False
+        model._initialize_bcs(bcs="damp")
+        if getattr(model.damp, '_profiles', None) is None:
+            return False
+        return plan_model(model.grid, so, model.nbl) is not None
+
+    # ------------------------------------------------------------------
+    def set_model(self, vp_dev=None):
+        """(Re)compute B = dt^2 vp^2 from the model's current velocity."""
+        vp_dev = self.model.vp._buf.dev() if vp_dev is None else vp_dev
+        _lib.check(_lib.lib().b2fwi_res2d_prepare(ctypes.byref(self.gs), _ptr(vp_dev), ctypes.c_float(self.dt),
+                                                  _ptr(self.B), _stream()))
+
+    def forward(self, save=False, illum=False):
+        """All shots forward: returns the device tensor rec[nshots, nt, nrec]."""
+        import torch
+        steps = self.nt - 2
+        if save and self.hist is None:
+            self.hist = torch.empty((self.nshots, steps) + self.wshape, dtype=torch.float32, device='cuda')
+        if illum and self.illum is None:
+            self.illum = torch.empty((self.nshots,) + self.wshape, dtype=torch.float32, device='cuda')
+        self.set_model()
+        _lib.check(_lib.lib().b2fwi_res2d_forward(
+            ctypes.byref(self.gs), ctypes.byref(self.plan), _ptr(self.B), _ptr(self.sx), _ptr(self.sz),
+            ctypes.c_float(self.dt), self.nt, 1, self.nt - 2, self.nshots, _ptr(self.src), 1,
+            self.maps_fwd.byref(), _ptr(self.rec), self.nrec, _ptr(self.hist) if save else None,
+            _ptr(self.illum) if illum else None, _stream()))
+        return self.rec
+
+    def gradient(self, residual):
+        """All shots backward + imaging from the saved history: returns grad[nshots, wx, wz4] (window layout)."""
+        import torch
+        assert self.hist is not None, "forward(save=True) first"
+        assert tuple(residual.shape) == (self.nshots, self.nt, self.nrec) and residual.is_contiguous()
+        if self.grad is None:
+            self.grad = torch.empty((self.nshots,) + self.wshape, dtype=torch.float32, device='cuda')
+        _lib.check(_lib.lib().b2fwi_res2d_gradient(
+            ctypes.byref(self.gs), ctypes.byref(self.plan), _ptr(self.B), _ptr(self.sx), _ptr(self.sz),
+            ctypes.c_float(self.dt), self.nt, 1, self.nt - 2, self.nshots, _ptr(residual), self.nrec,
+            self.maps_bwd.byref(), _ptr(self.hist), _ptr(self.grad), _stream()))
+        return self.grad
+
+    def crop(self, window_field):
+        """[.., wx, wz4] window layout -> [.., nx, nz] physical domain."""
+        nz = self.model.shape[1]
+        return window_field[..., self.col0:self.col0 + nz]
+
+    def window_mask_accumulate(self, field_s, mask, out):
+        """out[nx, nz] (fp64) += crop(field_s) * mask   (b2fwi_window_mask_accumulate)."""
+        nx, nz = self.model.shape
+        _lib.check(_lib.lib().b2fwi_window_mask_accumulate(nx, nz, _ptr(field_s), self.wshape[1], self.col0,
+                                                           _ptr(mask), _ptr(out), _stream()))
+
+
+def smoke_check(model, geom, d64, g64_full):
+    """Used by __graft_entry__.smoke(): the resident engine on the smoke shot against the oracle's
+    traces and (cropped) gradient."""
+    import torch
+    sv = ResidentSurvey(geom, [0])
+    rec = sv.forward(save=True, illum=True)[0].cpu().numpy()
+    res = torch.from_numpy(np.ascontiguousarray(d64, dtype=np.float32)[None]).cuda()
+    grad = sv.crop(sv.gradient(res))[0].cpu().numpy()
+    nbl = model.nbl
+    g64 = g64_full[nbl:-nbl, nbl:-nbl]
+    et = np.linalg.norm(rec - d64) / np.linalg.norm(d64)
+    eg = np.linalg.norm(grad - g64) / np.linalg.norm(g64)
+    print("smoke (resident engine, cluster=%d): traces rel-L2 %.2e, gradient rel-L2 %.2e" % (sv.plan.cluster, et, eg))
+    assert et <= 1e-5 and eg <= 1e-4

@@ -144,6 +144,85 @@ int b2fwi_geometry_mask(const b2fwi_grid *g, int32_t nbl, const double *pts, int
 int b2fwi_crop_mask_accumulate(const b2fwi_grid *g, int32_t nbl, const float *field,
                                const double *mask, double *out, void *stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * SM-resident 2-D engine: all time steps of all shots of a rank in ONE launch, one thread-block
+ * cluster per shot, wavefields in shared memory / registers (devito_fwi_b200/csrc/resident2d.cu).
+ * It computes exactly what b2fwi_forward / b2fwi_gradient compute for a zero initial state, for
+ * 2-D grids with space_order <= 8 and a separable damping profile (seismic/model.py:31-49), and is
+ * what fwi.py:fm_multi / fwi_obj_multi (the shot loops, fwi.py:67-81,183-199) run on.
+ * Only the imaging window [wx0,wx1) x quads [wq0,wq1) (the physical domain the reference crops the
+ * gradient to, fwi.py:166-167) is accumulated / stored.
+ */
+typedef struct b2fwi_res2d_plan {
+    int32_t cluster;          /* CTAs (SMs) per shot */
+    int32_t rows_per_thread;  /* P */
+    int32_t groups;           /* row groups per CTA */
+    int32_t threads;          /* threads per CTA */
+    int32_t rows_cta;         /* grid rows per CTA */
+    int32_t tile_rows;
+    int32_t smem_bytes;
+    int32_t wx0, wx1;         /* window rows, padded-grid coordinates */
+    int32_t wq0, wq1;         /* window columns in units of 4 cells (quads) */
+} b2fwi_res2d_plan;
+
+/* Host-built maps (devito_fwi_b200.resident), indexed by shot*cluster + rank; device pointers. */
+typedef struct b2fwi_res2d_maps {
+    const int32_t *inj_desc;   /* [.][2] ncell, cell_base */
+    const int32_t *inj_cptr;   /* CSR pointers per cell slot into inj_pt / inj_w */
+    const int32_t *inj_pt;     /* point index of each contribution, ascending within a cell */
+    const float *inj_w;        /* multilinear weight of each contribution */
+    const uint64_t *thr_mask;  /* [.][threads] bit r*4+j set: lane j of row r of the thread's strip is a cell */
+    const int32_t *thr_base;   /* [.][threads] first cell slot of the thread */
+    const int32_t *itp_desc;   /* [.][2] count, base  (receivers recorded by this CTA; forward only) */
+    const int32_t *itp_pt;     /* receiver index */
+    const int32_t *itp_off;    /* [.][4] float offsets into the CTA's shared tile, -1 = outside the grid */
+    const float *itp_w;        /* [.][4] */
+} b2fwi_res2d_maps;
+
+/* Decomposition of a 2-D grid onto clusters; window = the grid minus `nbl` cells on every side.
+ * min_cluster: smallest cluster size to try (1..8). Returns B2FWI_EUNSUPPORTED when nothing fits. */
+int b2fwi_res2d_plan_model(const b2fwi_grid *g, int32_t nbl, int32_t min_cluster, b2fwi_res2d_plan *plan_out);
+
+/* B = dt^2 vp^2 (fp64, rounded once) as a pitched slice. */
+int b2fwi_res2d_prepare(const b2fwi_grid *g, const float *vp, float dt, float *B_out, void *stream);
+
+/*
+ * Forward sweep of `nshots` shots (zero initial state), time_m..time_M:
+ *   src [nshots][nt][nsrc] -> rec [nshots][nt][nrec] (rows time_m..time_M written; may be NULL),
+ *   hist (nullable) [nshots][time_M-time_m+1][wx1-wx0][(wq1-wq0)*4]: u.dt2 of the window, slice t-time_m,
+ *   illum_out (nullable) [nshots][wx1-wx0][(wq1-wq0)*4]: sum_t u[t]^2 of the window (overwritten).
+ * sx [shape[0]], sz [4*ceil(shape[1]/4)]: the two parts of damp/dt.
+ */
+int b2fwi_res2d_forward(const b2fwi_grid *g, const b2fwi_res2d_plan *plan, const float *B, const float *sx,
+                        const float *sz, float dt, int32_t nt, int32_t time_m, int32_t time_M, int32_t nshots,
+                        const float *src, int32_t nsrc, const b2fwi_res2d_maps *maps,
+                        float *rec, int32_t nrec, float *hist, float *illum_out, void *stream);
+
+/*
+ * Backward sweep with imaging condition: res [nshots][nt][nrec] injected, hist as written by
+ * b2fwi_res2d_forward, grad_out [nshots][wx1-wx0][(wq1-wq0)*4] = -sum_t u.dt2[t] v[t] (overwritten).
+ */
+int b2fwi_res2d_gradient(const b2fwi_grid *g, const b2fwi_res2d_plan *plan, const float *B, const float *sx,
+                         const float *sz, float dt, int32_t nt, int32_t time_m, int32_t time_M, int32_t nshots,
+                         const float *res, int32_t nrec, const b2fwi_res2d_maps *maps,
+                         const float *hist, float *grad_out, void *stream);
+
+/*
+ * out[i,j] += field[i*row_stride + col0 + j] * mask[i,j], i < nx, j < nz: the crop + mute + shot sum of
+ * fwi.py:166-171,195-199 for a window-layout field. mask (fp64, nullable) from b2fwi_geometry_mask.
+ */
+int b2fwi_window_mask_accumulate(int32_t nx, int32_t nz, const float *field, int64_t row_stride, int32_t col0,
+                                 const double *mask, double *out, void *stream);
+
+/*
+ * On-device least-squares misfit (misfit/misfit.py:5-9 with the direct-wave subtraction of
+ * fwi.py:146-150): residual = (syn - dw) - (obs - dw) in fp32 (dw nullable), fval_out[0] += 0.5*sum residual^2
+ * accumulated in fp64 (deterministic two-stage reduction). n = elements.
+ */
+int b2fwi_l2_misfit(const float *syn, const float *obs, const float *dw, int64_t n, float *residual_out,
+                    double *fval_out, double *scratch /* >= 1024 doubles */, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

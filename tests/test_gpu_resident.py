@@ -1,0 +1,117 @@
+"""GPU parity of the SM-resident 2-D engine (one cluster per shot, all shots in one launch) against
+the fp64 oracle and against the per-step streaming engine, on the named 2-D configurations."""
+import numpy as np
+import pytest
+
+from tests.util import ref_model, rel_l2
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+
+TOL_TRACE = 1e-5
+TOL_GRAD = 1e-4
+
+
+def _oracle_shot(geom_true, geom_init, i):
+    rm_true, rm_init = ref_model(geom_true.model), ref_model(geom_init.model)
+    nt, dt = geom_init.nt, float(geom_init.dt)
+    wav = np.float64(geom_init.src.data[:, :1])
+    o64, _ = ref.forward(rm_true, geom_true.src_positions[i], geom_true.rec_positions, wav, nt, dt)
+    s64, u64 = ref.forward(rm_init, geom_init.src_positions[i], geom_init.rec_positions, wav, nt, dt, save=True)
+    g64 = ref.gradient(rm_init, s64 - o64, geom_init.rec_positions, u64, nt, dt)
+    illum = (u64 * u64).sum(axis=0)
+    return o64, s64, g64, illum
+
+
+@pytest.mark.parametrize("config", ["marmousi", "circle6", "circle4", "marmousi2"])
+def test_resident_engine_vs_oracle(config):
+    import torch
+    import devito_fwi_b200 as b
+    from devito_fwi_b200 import configs
+    from devito_fwi_b200.resident import ResidentSurvey
+    if config == "marmousi":
+        g_true, g_init = configs.marmousi()[:2]
+        shots = [0, 14, 28]
+    elif config == "marmousi2":
+        g_true, g_init = configs.marmousi2()[:2]
+        shots = [7]
+    else:
+        g_true, g_init = configs.circle(space_order=6 if config == "circle6" else 4)
+        shots = [0, 5]
+    assert ResidentSurvey.supported(g_init)
+    sv_true = ResidentSurvey(g_true, shots)
+    sv = ResidentSurvey(g_init, shots)
+    obs = sv_true.forward().clone()
+    syn = sv.forward(save=True, illum=True).clone()
+    res = (syn - obs).contiguous()
+    grad = sv.crop(sv.gradient(res)).cpu().numpy()
+    illum = sv.crop(sv.illum).cpu().numpy()
+    # determinism: a second run is bitwise identical
+    syn2 = sv.forward(save=True, illum=True)
+    assert torch.equal(syn, syn2)
+    grad2 = sv.crop(sv.gradient(res)).cpu().numpy()
+    assert np.array_equal(grad, grad2)
+    nbl = g_init.model.nbl
+    for k, i in enumerate(shots):
+        o64, s64, g64, il64 = _oracle_shot(g_true, g_init, i)
+        et, eo = rel_l2(syn[k].cpu().numpy(), s64), rel_l2(obs[k].cpu().numpy(), o64)
+        # gradient driven by the oracle's own residual, to separate it from the trace error
+        res64 = torch.from_numpy(np.float32(s64 - o64)[None]).cuda()
+        print("%s shot %d (cluster=%d): traces %.2e / %.2e  illum %.2e" % (
+            config, i, sv.plan.cluster, et, eo, rel_l2(illum[k], il64[nbl:-nbl, nbl:-nbl])))
+        assert et <= TOL_TRACE and eo <= TOL_TRACE
+        assert rel_l2(illum[k], il64[nbl:-nbl, nbl:-nbl]) <= TOL_GRAD
+        eg = rel_l2(grad[k], g64[nbl:-nbl, nbl:-nbl])
+        print("   gradient (own residual) %.2e" % eg)
+        assert eg <= 5 * TOL_GRAD       # includes the amplified trace difference in the residual
+    # same residual on both sides -> the gradient tolerance proper
+    o64, s64, g64, _ = _oracle_shot(g_true, g_init, shots[0])
+    res_all = res.clone()
+    res_all[0] = torch.from_numpy(np.float32(s64 - o64)).cuda()
+    g0 = sv.crop(sv.gradient(res_all.contiguous()))[0].cpu().numpy()
+    eg = rel_l2(g0, g64[nbl:-nbl, nbl:-nbl])
+    print("   gradient (oracle residual) %.2e" % eg)
+    assert eg <= TOL_GRAD
+
+
+def test_objective_resident_vs_streaming_vs_oracle():
+    """fwi_obj_multi / fwi_loss on Marmousi (5 shots, direct-wave subtraction, bathymetry mask,
+    illumination preconditioning): resident engine + on-device L2 misfit == streaming engine + host
+    plug-in misfit == numpy restatement of fwi.py."""
+    import devito_fwi_b200 as b
+    from devito_fwi_b200 import configs, fwi
+    g_true, g_init, g_const, mask = configs.marmousi(nsrc=5)
+    obs = fwi.fm_multi(g_true)
+    dw = fwi.fm_multi(g_const)
+    x = 1. / (g_init.model.vp.data[40:-40, 40:-40].astype(np.float64) ** 2)
+    f_r, g_r, res_r = fwi.fwi_loss(x.ravel(), g_init, obs, fwi.least_square, dw, mask, True, True)
+    assert len(res_r) == 5 and np.asarray(res_r[0]).shape == (g_init.nt, 300)
+
+    def host_misfit(syn, o):       # a plug-in the engine cannot recognise -> host round trip
+        r = syn - o
+        return .5 * np.linalg.norm(r.flatten()) ** 2, r
+    f_h, g_h, _ = fwi.fwi_loss(x.ravel(), g_init, obs, host_misfit, dw, mask, True, True)
+    fwi.ENGINE = 'stream'
+    try:
+        f_s, g_s, _ = fwi.fwi_loss(x.ravel(), g_init, obs, fwi.least_square, dw, mask, True, True)
+    finally:
+        fwi.ENGINE = 'auto'
+    print("resident vs host-misfit: f %.2e g %.2e | resident vs streaming: f %.2e g %.2e" % (
+        abs(f_r - f_h) / f_h, rel_l2(g_r, g_h), abs(f_r - f_s) / f_s, rel_l2(g_r, g_s)))
+    assert abs(f_r - f_h) / f_h < 1e-5 and rel_l2(g_r, g_h) < 1e-6   # host misfit sums in fp32
+    assert abs(f_r - f_s) / f_s < 1e-4 and rel_l2(g_r, g_s) < 2 * TOL_GRAD
+
+    rm_true, rm_init, rm_const = (ref_model(g.model) for g in (g_true, g_init, g_const))
+    nt, dt = g_init.nt, float(g_init.dt)
+    wav = np.float64(g_init.src.data[:, :1])
+    fw = lambda rm: [ref.forward(rm, g_init.src_positions[i], g_init.rec_positions, wav, nt, dt)[0]  # noqa: E731
+                     for i in range(5)]
+    f64, g64, _ = ref.fwi_obj_multi(rm_init, g_init.src_positions, g_init.rec_positions, wav, nt, dt,
+                                    fw(rm_true), direct_wave=fw(rm_const), mask=mask, precond=True,
+                                    calc_grad=True)
+    print("resident vs oracle: f %.2e g %.2e" % (abs(f_r - f64) / f64, rel_l2(g_r, g64)))
+    assert abs(f_r - f64) / f64 <= 1e-4
+    assert rel_l2(g_r, g64) <= 5 * TOL_GRAD
+    # forward-only evaluation of the line search
+    f2, g2, _ = fwi.fwi_loss(x.ravel(), g_init, obs, fwi.least_square, dw, mask, True, False)
+    assert np.isclose(f2, f_r, rtol=1e-9) and not g2.any()
