@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- FWI-gradient throughput of the B200 path on the reference's Marmousi configuration.
+
+Workload (BASELINE.json configs[2], marmousi_fwi.py): SMARMN 300x106 (+2*40 sponge = 380x186), h = 30 m,
+space_order 8, dt = 2.95 ms, tn = 4000 ms (nt = 1357), 29 shots x 300 receivers, L2 misfit with
+direct-wave subtraction, bathymetry mask and illumination preconditioning. One "step" = one evaluation of
+the objective and its gradient over the whole survey, i.e. the reference's
+    fwi_loss(x, geometry, obs, least_square, direct_wave, mask, precond=True)        (fwi.py:236-246)
+Weak scaling: every rank (GPU) owns one full 29-shot survey (29*N shots in the job); the ranks'
+[grad | illum | fval] are summed with ONE NCCL all-reduce per step, as fwi_obj_multi does.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--extra]
+    torchrun --nproc-per-node N bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0). `value` = grid-point-steps per second of the whole job with observed data
+already resident in HBM; `e2e` = the same through the public API with HOST buffers (H2D of the observed and
+direct-wave records and of the model, D2H of (f, g)) inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHOTS_PER_RANK = 29
+BYTES_FWD, BYTES_ADJ = 20, 32      # algorithmic bytes per grid-point-step (SURVEY.md section 8d / DESIGN.md)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[5 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def make_survey(world):
+    """Marmousi geometries with SHOTS_PER_RANK * world shots (each rank gets the 29 positions of the
+    reference's acquisition through the round-robin partition i % world == rank)."""
+    from devito_fwi_b200 import configs
+    from devito_fwi_b200.geometry import AcquisitionGeometry
+    g_true, g_init, g_const, mask = configs.marmousi(nsrc=SHOTS_PER_RANK)
+    if world > 1:
+        src = np.repeat(g_true.src_positions, world, axis=0)
+        mk = lambda g: AcquisitionGeometry(g.model, g.rec_positions, src, g.t0, g.tn, f0=g.f0,  # noqa: E731
+                                           src_type=g.src_type)
+        g_true, g_init, g_const = mk(g_true), mk(g_init), mk(g_const)
+    return g_true, g_init, g_const, mask
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import devito_fwi_b200 as b
+    from devito_fwi_b200 import fwi, _lib
+    from devito_fwi_b200 import dist as bdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        bdist.init_from_env("nccl")
+    lib = _lib.lib()
+
+    g_true, g_init, g_const, mask = make_survey(world)
+    model = g_init.model
+    npts = int(np.prod(model.grid.shape))
+    nt, nrec = g_init.nt, g_init.nrec
+    steps_per_sweep = nt - 2
+    nshots_job = g_init.nsrc
+    my_shots = bdist.local_shots(nshots_job)
+
+    # ---- set-up (untimed): observed and direct-wave data of this rank's shots, host + device copies
+    from devito_fwi_b200.resident import ResidentSurvey
+    obs, dw = [None] * nshots_job, [None] * nshots_job
+    for geom, store in ((g_true, obs), (g_const, dw)):
+        sv = ResidentSurvey(geom, my_shots)
+        rec = sv.forward().clone()
+        for k, i in enumerate(my_shots):
+            r = b.Receiver(name='rec', grid=geom.grid, time_range=geom.time_axis, coordinates=geom.rec_positions)
+            r.data[:] = rec[k].cpu().numpy()
+            r._sdata.dev()
+            store[i] = r
+        del sv
+    x0 = (1. / (model.vp.data[model.nbl:-model.nbl, model.nbl:-model.nbl].astype(np.float64) ** 2)).ravel()
+
+    def step(host_buffers):
+        if host_buffers:
+            for i in my_shots:          # the caller hands HOST arrays: invalidate the device copies
+                obs[i].data
+                dw[i].data
+        return fwi.fwi_loss(x0, g_init, obs, fwi.least_square, dw, mask, True, True)
+
+    def timed(n, host_buffers):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.b2fwi_launch_count()
+        e0.record()
+        for _ in range(n):
+            f, g, _ = step(host_buffers)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), lib.b2fwi_launch_count() - l0, (f, g)
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, launches, (fval, grad) = timed(args.steps, host_buffers=False)
+    for _ in range(2):
+        step(True)
+    ms_e2e, _, _ = timed(args.steps, host_buffers=True)
+
+    # ---- per-kernel roofline, measured live with CUDA events on the launching stream
+    survey = fwi._resident_survey(g_init, my_shots)
+    peak, peak_src = peaks()
+    kern = {}
+    if survey is not None:
+        res = survey._res
+        for name, fn, bpp in (("res2d_kernel<fwd>", lambda: survey.forward(save=True, illum=True), BYTES_FWD),
+                              ("res2d_kernel<adj+img>", lambda: survey.gradient(res), BYTES_ADJ)):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            alg = float(bpp) * npts * steps_per_sweep * len(my_shots)
+            kern[name] = {"ms_per_launch": round(ms, 4), "algorithmic_GB": round(alg / 1e9, 3),
+                          "achieved": round(alg / ms / 1e6, 1), "gpts_per_s": round(alg / bpp / ms / 1e6, 1)}
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        return
+    work = 2.0 * npts * steps_per_sweep * nshots_job            # forward + adjoint grid-point-steps per step
+    ms_step = ms_dev / args.steps
+    ms_step_e2e = ms_e2e / args.steps
+    out = {
+        "metric": "FWI gradient throughput: fwd+adj stencil grid-point-steps per second, whole job",
+        "value": round(work / ms_step / 1e6, 2), "unit": "Gpts/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "shots_per_s": round(nshots_job / ms_step * 1e3, 1),
+        "config": {"workload": "marmousi_fwi (BASELINE.json configs[2]): 380x186 padded, so=8, nt=1357, "
+                               "%d shots/GPU x 300 rec, L2 + direct-wave + mask + illumination precond" % SHOTS_PER_RANK,
+                   "shots_total": nshots_job, "engine": "resident2d" if survey is not None else "streaming",
+                   "cluster_per_shot": int(survey.plan.cluster) if survey is not None else None,
+                   "l2": "no explicit flush: each step streams a %.1f GB u.dt2 history through HBM (>> 126 MB L2)"
+                         % (len(my_shots) * steps_per_sweep * 300 * 108 * 4 * 2 / 1e9),
+                   "allreduce": "1 x NCCL sum of [grad|illum|fval] (%d doubles) per step" % (2 * 300 * 106 + 1)},
+        "e2e": {"value": round(work / ms_step_e2e / 1e6, 2), "unit": "Gpts/s", "ms_per_step": round(ms_step_e2e, 3),
+                "shots_per_s": round(nshots_job / ms_step_e2e * 1e3, 1),
+                "h2d_bytes_per_step": int(len(my_shots) * 2 * nt * nrec * 4 + npts * 4),
+                "d2h_bytes_per_step": int((2 * 300 * 106 + 1) * 8),
+                "note": "fwi_loss() with host obs / direct-wave records (pinned) and host model; residual list "
+                        "stays on the device until read (LazyResidual)"},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "objective": {"fval": float(fval), "grad_absmax": float(np.abs(grad).max())},
+    }
+    if kern:
+        dom = max(kern, key=lambda k: kern[k]["ms_per_launch"])
+        out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved"], "peak": peak,
+                           "unit": "GB/s", "frac": round(kern[dom]["achieved"] / peak, 3), "traffic": None,
+                           "peak_source": peak_src,
+                           "note": "algorithmic bytes (20 B fwd / 32 B adj+img per grid-point-step) over the live "
+                                   "CUDA-event duration; the 2-D wavefields are SM-resident (shared memory + "
+                                   "registers), so the fraction may exceed 1: HBM is not the binding roof here, "
+                                   "FP32 issue is (see DESIGN.md)",
+                           "kernels": kern}
+    if world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(sample_shots=8)
+    if args.extra:
+        out["extra"] = extra_3d()
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_gradient_shots(shot_ids, fast=True):
+    """Oracle (CPU restatement, OpenMP) forward(save) + gradient of Marmousi shots; returns seconds."""
+    from oracle import ref
+    from devito_fwi_b200 import configs
+    shape, spacing, nbl = (300, 106), (30., 30.), 40
+    vp_true = configs.load_vp('SMARMN', 'vp.true', shape)
+    vp_init = configs.load_vp('SMARMN', 'vp.smooth_20', shape)
+    rm_true = ref.RefModel((0., 0.), spacing, shape, 8, vp_true, nbl=nbl, dt=2.95)
+    rm_init = ref.RefModel((0., 0.), spacing, shape, 8, vp_init, nbl=nbl, dt=2.95)
+    nt, _, tv = ref.time_axis(0., 4000., 2.95)
+    wav = ref.ricker(0.007, tv).astype(np.float32)
+    src = np.stack([np.linspace(0, 8970., SHOTS_PER_RANK), np.full(SHOTS_PER_RANK, 60.)], axis=1)
+    rec = np.stack([np.linspace(30., 8940., 300), np.full(300, 60.)], axis=1)
+    ref.lib(fast)
+    obs = [ref.forward(rm_true, src[i], rec, wav, nt, 2.95, fast=fast)[0] for i in shot_ids]
+    t0 = time.perf_counter()
+    for k, i in enumerate(shot_ids):
+        syn, u = ref.forward(rm_init, src[i], rec, wav, nt, 2.95, save=True, fast=fast)
+        ref.gradient(rm_init, syn - obs[k], rec, u, nt, 2.95, fast=fast)
+    return time.perf_counter() - t0, int(np.prod(rm_init.shape_pml)), nt
+
+
+def cpu_baseline(sample_shots=2):
+    cores = os.cpu_count() or 1
+    sec, npts, nt = cpu_gradient_shots(list(range(sample_shots)))     # includes first-touch warm-up
+    sec, npts, nt = cpu_gradient_shots(list(range(sample_shots)))
+    work = 2.0 * npts * (nt - 2) * sample_shots
+    return {"value": round(work / sec / 1e9, 3), "unit": "Gpts/s", "cores": cores, "kind": "port",
+            "shots_per_s": round(sample_shots / sec, 3),
+            "sample": "%d Marmousi shot-gradients (forward with saved history + adjoint/imaging), "
+                      "oracle/fwi_oracle.c built -O3 -march=native -ffast-math -fopenmp (Devito's flag set), "
+                      "%d OpenMP threads; CPU restatement, not Devito" % (sample_shots, cores)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path. Devito itself is neither vendored
+    nor installable offline, so this times the oracle port with all host threads (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    sample = 8
+    cpu_gradient_shots([0])        # warm-up: build the library, touch memory
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_gradient_shots(list(range(sample)))
+    t = 0.0
+    for _ in range(args.steps):
+        sec, npts, nt = cpu_gradient_shots(list(range(sample)))
+        t += sec
+    work = 2.0 * npts * (nt - 2) * sample * args.steps
+    v = round(work / t / 1e9, 3)
+    out = {"impl": "reference",
+           "metric": "FWI gradient throughput: fwd+adj stencil grid-point-steps per second, whole job",
+           "value": v, "unit": "Gpts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(t / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "shots_per_s": round(sample * args.steps / t, 3),
+           "config": {"workload": "marmousi_fwi (BASELINE.json configs[2]): 380x186 padded, so=8, nt=1357, "
+                                  "%d shots/GPU x 300 rec" % SHOTS_PER_RANK,
+                      "sample_shots_per_step": sample},
+           "cpu_baseline": {"value": v, "unit": "Gpts/s", "cores": cores, "kind": "port",
+                            "sample": "each step = %d Marmousi shot-gradients of the 29-shot survey on %d OpenMP "
+                                      "threads (oracle port, Devito flag set); Devito is not installable here"
+                                      % (sample, cores)},
+           "e2e": {"value": v, "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def extra_3d():
+    """Secondary workload: 3-D layered 512^3 (+2*40), so=8: streaming-engine step kernels vs the HBM roofline."""
+    import torch
+    import devito_fwi_b200 as b
+    from devito_fwi_b200 import configs
+    peak, _ = peaks()
+    geom = configs.layered3d(n=512, space_order=8, rec_decimate=4)
+    solver = b.AcousticWaveSolver(geom.model, geom, space_order=8)
+    u = b.TimeFunction(name='u', grid=geom.model.grid, time_order=2, space_order=8)
+    solver.forward(u=u, time_M=6)
+    _, _, s = solver.forward(u=u, time_m=7, time_M=26)
+    torch.cuda.empty_cache()
+    return {"workload": "layered3d 592^3 so=8 forward step (streaming engine)", "gpts_per_s": round(s.gpointss, 1),
+            "achieved_GBs": round(s.gbytess, 1), "frac_of_measured_hbm": round(s.gbytess / peak, 3)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--extra", action="store_true", help="also time the 3-D streaming kernels")
+    args = ap.parse_args()
+    import warnings
+    warnings.filterwarnings("ignore")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

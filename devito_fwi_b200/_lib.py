@@ -77,6 +77,7 @@ PROTOTYPES = {
     # name: (restype, argtypes)   -- must list every symbol declared in include/b2fwi.h
     "b2fwi_version": (_I, []),
     "b2fwi_last_error": (ctypes.c_char_p, []),
+    "b2fwi_launch_count": (ctypes.c_int64, []),
     "b2fwi_field_layout": (ctypes.c_int, [_G, ctypes.POINTER(ctypes.c_int64 * 3),
                                           ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "b2fwi_prepare_coeffs": (ctypes.c_int, [_G, _P, _P, _F, _P, _P]),
@@ -90,6 +91,7 @@ PROTOTYPES = {
     "b2fwi_res2d_forward": (ctypes.c_int, [_G, _P, _P, _P, _P, _F, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P]),
     "b2fwi_res2d_gradient": (ctypes.c_int, [_G, _P, _P, _P, _P, _F, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P]),
     "b2fwi_window_mask_accumulate": (ctypes.c_int, [_I, _I, _P, ctypes.c_int64, _I, _P, _P, _P]),
+    "b2fwi_window_mask_accumulate_batch": (ctypes.c_int, [_I, _I, _I, _P, ctypes.c_int64, ctypes.c_int64, _I, _P, _P, _P]),
     "b2fwi_l2_misfit": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, _P, _P, _P]),
 }
 

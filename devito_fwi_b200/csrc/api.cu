@@ -1,6 +1,7 @@
 // api.cu -- extern "C" entry points of libb2fwi.so (see include/b2fwi.h) and the host-side
 // time loops of the streaming engine.
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -9,6 +10,9 @@
 namespace b2fwi {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...)
 {
@@ -104,6 +108,8 @@ extern "C" {
 int32_t b2fwi_version(void) { return B2FWI_VERSION; }
 
 const char *b2fwi_last_error(void) { return g_err; }
+
+int64_t b2fwi_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int b2fwi_field_layout(const b2fwi_grid *g, int64_t stride_out[3], int64_t *base_out, int64_t *elems_out)
 {

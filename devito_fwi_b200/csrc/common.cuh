@@ -11,6 +11,7 @@
 namespace b2fwi {
 
 void set_error(const char *fmt, ...);
+void count_launch(int n = 1);   // bookkeeping behind b2fwi_launch_count()
 
 #define B2_CHECK_ARG(cond, ...)              \
     do {                                     \

@@ -34,6 +34,22 @@ __global__ void window_mask_acc_kernel(int nx, int nz, const float *__restrict__
     out[idx] += mask ? f * mask[idx] : f;
 }
 
+// out[i,j] += sum_s field[s][i][col0+j] * mask[s][i][j], shots in ascending order (deterministic)
+__global__ void window_mask_acc_batch_kernel(int nshots, int nx, int nz, const float *__restrict__ field,
+                                             int64_t shot_stride, int64_t row_stride, int col0,
+                                             const double *__restrict__ mask, double *__restrict__ out)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nx * nz) return;
+    const int i = idx / nz, j = idx - i * nz;
+    double acc = out[idx];
+    for (int s = 0; s < nshots; s++) {
+        const double f = (double)field[s * shot_stride + (int64_t)i * row_stride + col0 + j];
+        acc += mask ? f * mask[(int64_t)s * nx * nz + idx] : f;
+    }
+    out[idx] = acc;
+}
+
 // stage 1: per-block partial sums (fixed order), stage 2: one block adds them up in index order
 __global__ void l2_stage1(const float *__restrict__ syn, const float *__restrict__ obs, const float *__restrict__ dw,
                           int64_t n, float *__restrict__ res, double *__restrict__ partial)
@@ -160,6 +176,7 @@ int b2fwi_res2d_prepare(const b2fwi_grid *g, const float *vp, float dt, float *B
     B2_CHECK_ARG(vp && B_out && dt > 0.f, "bad argument");
     bcoef_kernel<<<(unsigned)((L.elems + 255) / 256), 256, 0, (cudaStream_t)stream>>>(vp, (double)dt, B_out, L.elems);
     B2_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -218,6 +235,18 @@ int b2fwi_window_mask_accumulate(int32_t nx, int32_t nz, const float *field, int
     window_mask_acc_kernel<<<(nx * nz + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nx, nz, field, row_stride, col0, mask,
                                                                                   out);
     B2_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int b2fwi_window_mask_accumulate_batch(int32_t nshots, int32_t nx, int32_t nz, const float *field, int64_t shot_stride,
+                                       int64_t row_stride, int32_t col0, const double *mask, double *out, void *stream)
+{
+    B2_CHECK_ARG(nshots > 0 && nx > 0 && nz > 0 && field && out, "bad argument");
+    window_mask_acc_batch_kernel<<<(nx * nz + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        nshots, nx, nz, field, shot_stride, row_stride, col0, mask, out);
+    B2_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -230,6 +259,7 @@ int b2fwi_l2_misfit(const float *syn, const float *obs, const float *dw, int64_t
     l2_stage1<<<nblocks, 256, 0, (cudaStream_t)stream>>>(syn, obs, dw, n, residual_out, scratch);
     l2_stage2<<<1, 32, 0, (cudaStream_t)stream>>>(scratch, nblocks, fval_out);
     B2_CUDA(cudaGetLastError());
+    count_launch(2);
     return 0;
 }
 

@@ -300,6 +300,7 @@ static int launch_one(const Res2dArgs &a, cudaStream_t st)
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     B2_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    count_launch();
     return 0;
 }
 

@@ -236,6 +236,7 @@ static int launch_step_img(const Layout &L, const StepArgs &a, int img, dim3 gri
     default: set_error("bad imaging mode %d", img); return B2FWI_EINVAL;
     }
     B2_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -326,6 +327,7 @@ int launch_inject(float *field, const float *vp, float dt, const float *vals, co
     inject_kernel<<<(m->ncell + 127) / 128, 128, 0, st>>>(field, vp, dt, vals, m->ncell, m->cell_off, m->cell_ptr,
                                                         m->contrib_pt, m->contrib_w, d2u, cur, prev, inv_dt2);
     B2_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -335,6 +337,7 @@ int launch_interp(const float *field, float *out, const b2fwi_sparse *m, cudaStr
     interp_kernel<<<(m->npoint + 127) / 128, 128, 0, st>>>(field, out, m->npoint, m->ncorner, m->corner_off,
                                                          m->corner_w);
     B2_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -362,6 +365,7 @@ int launch_coeffs(const Layout &L, const float *vp, const float *damp, float dt,
     const int64_t n = L.elems;
     coeff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(vp, damp, (double)dt, coef, coef + n, n);
     B2_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -375,6 +379,7 @@ int launch_accum_sq(const Layout &L, float *acc, const float *f, cudaStream_t st
 {
     accum_sq_kernel<<<(unsigned)((L.elems + 255) / 256), 256, 0, st>>>(acc, f, L.elems);
     B2_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -413,6 +418,7 @@ int launch_geometry_mask(const b2fwi_grid *g, int nbl, const double *pts, int np
     geometry_mask_kernel<<<(nx * nz + 127) / 128, 128, 0, st>>>(nx, nz, (double)g->spacing[0], (double)g->spacing[1],
                                                               pts, npts, mask);
     B2_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -422,6 +428,7 @@ int launch_crop_mask_acc(const b2fwi_grid *g, const Layout &L, int nbl, const fl
     const int nx = g->shape[0] - 2 * nbl, nz = g->shape[1] - 2 * nbl;
     crop_mask_acc_kernel<<<(nx * nz + 127) / 128, 128, 0, st>>>(nx, nz, nbl, L.sr, L.base, field, mask, out);
     B2_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 

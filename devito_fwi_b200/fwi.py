@@ -265,7 +265,8 @@ def _stack_dev(receivers, shots, cache_owner, tag):
     import torch
     cache = cache_owner.__dict__.setdefault('_dev_stacks', {})
     hit = cache.get(tag)
-    if hit is not None and hit[0] is receivers and hit[1] == tuple(shots):
+    if hit is not None and hit[0] is receivers and hit[1] == tuple(shots) and \
+            all(receivers[i]._sdata._newer is None and receivers[i]._sdata._dev is not None for i in shots):
         return hit[2]
     t = torch.stack([receivers[i]._sdata.dev() for i in shots]).contiguous()
     cache[tag] = (receivers, tuple(shots), t)
@@ -309,10 +310,8 @@ def _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_gr
         residuals = [res_h[k] for k in range(len(shots))]
     if calc_grad:
         grad = survey.gradient(residual)
-        for k, i in enumerate(shots):
-            mask = _geometry_mask(_shot_geometry(geometry, i))
-            survey.window_mask_accumulate(grad[k], mask, acc[0])
-            survey.window_mask_accumulate(survey.illum[k], mask, acc[1])
+        survey.window_mask_accumulate_all(grad, acc[0])
+        survey.window_mask_accumulate_all(survey.illum, acc[1])
     return fval, residuals
 
 

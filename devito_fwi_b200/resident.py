@@ -253,6 +253,28 @@ class ResidentSurvey(object):
         nz = self.model.shape[1]
         return window_field[..., self.col0:self.col0 + nz]
 
+    def masks(self):
+        """fp64 mute masks of all shots, [nshots, nx, nz] (b2fwi_geometry_mask; geometry-only, built once)."""
+        import torch
+        if getattr(self, '_masks', None) is None:
+            nx, nz = self.model.shape
+            m = torch.empty((self.nshots, nx, nz), dtype=torch.float64, device='cuda')
+            for k, i in enumerate(self.shots):
+                pts = np.ascontiguousarray(np.concatenate([self.geometry.src_positions[i:i + 1],
+                                                           self.geometry.rec_positions]), dtype=np.float64)
+                pts_dev = torch.from_numpy(pts).cuda()
+                _lib.check(_lib.lib().b2fwi_geometry_mask(ctypes.byref(self.gs), self.model.nbl, _ptr(pts_dev),
+                                                          pts.shape[0], _ptr(m[k]), _stream()))
+            self._masks = m
+        return self._masks
+
+    def window_mask_accumulate_all(self, field, out, use_mask=True):
+        """out[nx, nz] (fp64) += sum_shots crop(field[s]) * mask[s]."""
+        nx, nz = self.model.shape
+        _lib.check(_lib.lib().b2fwi_window_mask_accumulate_batch(
+            self.nshots, nx, nz, _ptr(field), self.wshape[0] * self.wshape[1], self.wshape[1], self.col0,
+            _ptr(self.masks()) if use_mask else None, _ptr(out), _stream()))
+
     def window_mask_accumulate(self, field_s, mask, out):
         """out[nx, nz] (fp64) += crop(field_s) * mask   (b2fwi_window_mask_accumulate)."""
         nx, nz = self.model.shape

@@ -73,6 +73,8 @@ typedef struct b2fwi_sparse {
 
 int32_t b2fwi_version(void);
 const char *b2fwi_last_error(void);
+/* Number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t b2fwi_launch_count(void);
 
 /* Layout of one haloed slice: element strides per dimension, offset of domain cell (0,..,0), total floats. */
 int b2fwi_field_layout(const b2fwi_grid *g, int64_t stride_out[3], int64_t *base_out, int64_t *elems_out);
@@ -214,6 +216,11 @@ int b2fwi_res2d_gradient(const b2fwi_grid *g, const b2fwi_res2d_plan *plan, cons
  */
 int b2fwi_window_mask_accumulate(int32_t nx, int32_t nz, const float *field, int64_t row_stride, int32_t col0,
                                  const double *mask, double *out, void *stream);
+
+/* Same, summed over `nshots` window-layout fields (shot stride in floats) with per-shot masks
+ * mask[nshots][nx][nz]; shots are added in ascending order. */
+int b2fwi_window_mask_accumulate_batch(int32_t nshots, int32_t nx, int32_t nz, const float *field, int64_t shot_stride,
+                                       int64_t row_stride, int32_t col0, const double *mask, double *out, void *stream);
 
 /*
  * On-device least-squares misfit (misfit/misfit.py:5-9 with the direct-wave subtraction of

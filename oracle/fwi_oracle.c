@@ -31,6 +31,17 @@
 
 #define ORACLE_MAX_R 8
 
+/* The *_fast build (timed CPU baseline only) flushes denormals like Devito's generated code does
+ * (sa_01_iso_implementation1.ipynb:1222-1224: _MM_SET_DENORMALS_ZERO_MODE / _MM_SET_FLUSH_ZERO_MODE);
+ * without it the exponentially small wavefront tail runs in microcode. MXCSR is per thread, so it is set
+ * inside the parallel loops. The strict build (the parity checker) keeps IEEE gradual underflow. */
+#if defined(ORACLE_FTZ) && (defined(__x86_64__) || defined(__i386__))
+#include <xmmintrin.h>
+#define ORACLE_SET_FTZ() _mm_setcsr(_mm_getcsr() | 0x8040)
+#else
+#define ORACLE_SET_FTZ() ((void)0)
+#endif
+
 typedef struct {
     int ndim;        /* 2 or 3 */
     int shape[3];    /* padded grid points per dimension, last dimension contiguous */
