@@ -63,6 +63,46 @@ static __device__ __forceinline__ float rcp_approx(float x)
     return r;
 }
 
+// ---- raw shared / distributed-shared accessors on 32-bit addresses (no generic-address arithmetic in the hot loop)
+static __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ float4 lds4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+static __device__ __forceinline__ float lds1(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+static __device__ __forceinline__ void sts4(uint32_t addr, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+static __device__ __forceinline__ void sts4_cluster(uint32_t addr, float4 v)
+{
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+static __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+static __device__ __forceinline__ void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Hide a value from the optimiser: stops ptxas/nvvm from strength-reducing the per-row addresses of the
+// unrolled row loop into P separately carried registers (which spilled the register-resident state).
+static __device__ __forceinline__ void opaque(uint32_t &x) { asm volatile("" : "+r"(x)); }
+template <typename T>
+static __device__ __forceinline__ void opaque_ptr(T *&p) { asm volatile("" : "+l"(p)); }
+
 template <int P>
 struct MaxThreads { static constexpr int value = (P <= 8) ? 480 : (P <= 12) ? 384 : 288; };
 
@@ -100,15 +140,25 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     for (int i = tid; i < a.G * P; i += blockDim.x) sxs[i] = (row0 + i < a.nx && i < rows_valid) ? a.sx[row0 + i] : 0.f;
 
     // ---- per-thread persistent state
-    float4 dl[P], Bq[P];
+    // delta lives in registers; B = dt^2 vp^2 is re-read from L2 every step with a two-row prefetch
+    // (holding it in registers as well spills: 2 x P float4 + the 2R+1-row window exceed the budget)
+    float4 dl[P];
+    unsigned vmask = 0, wmask = 0, pprev = 0, pnext = 0;    // per-row flags, bit r
+    const float4 *Bp = reinterpret_cast<const float4 *>(a.B + (int64_t)(row0 + lr0) * a.sr + 4 * qi);
+    const int64_t Bstride = a.sr / 4;                        // row stride in float4
 #pragma unroll
     for (int r = 0; r < P; r++) {
         dl[r] = z4();
-        const bool ok = tactive && (lr0 + r < rows_valid);
-        Bq[r] = ok ? __ldg(reinterpret_cast<const float4 *>(a.B + (int64_t)(row0 + lr0 + r) * a.sr + 4 * qi)) : z4();
+        const int lr = lr0 + r, row = row0 + lr;
+        const bool ok = tactive && (lr < rows_valid);
+        if (ok) {
+            vmask |= 1u << r;
+            if (qi >= a.wq0 && qi < a.wq1 && row >= a.wx0 && row < a.wx1) wmask |= 1u << r;
+            if (lr < R && crank > 0) pprev |= 1u << r;
+            if (lr >= rows_valid - R && crank < a.C - 1) pnext |= 1u << r;
+        }
     }
     const float4 szq = tactive ? __ldg(reinterpret_cast<const float4 *>(a.sz + 4 * qi)) : z4();
-    const bool qin = tactive && qi >= a.wq0 && qi < a.wq1;
     const unsigned long long imask = tactive ? a.thr_mask[(int64_t)sc * T + tid] : 0ull;
     const int ibase = tactive ? a.thr_base[(int64_t)sc * T + tid] : 0;
 
@@ -122,28 +172,40 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
         return v;
     };
 
-    // remote views of the neighbours' tiles (distributed shared memory)
-    float *prev0 = (crank > 0) ? cluster.map_shared_rank(tile0, crank - 1) : nullptr;
-    float *prev1 = (crank > 0) ? cluster.map_shared_rank(tile1, crank - 1) : nullptr;
-    float *next0 = (crank < a.C - 1) ? cluster.map_shared_rank(tile0, crank + 1) : nullptr;
-    float *next1 = (crank < a.C - 1) ? cluster.map_shared_rank(tile1, crank + 1) : nullptr;
+    // ---- 32-bit shared addresses (bytes); everything below is an offset from these
+    const uint32_t pitchB = (uint32_t)pitch * 4u;
+    const uint32_t own_off = (uint32_t)(lr0 + R) * pitchB + (uint32_t)qi * 16u;     // own row 0 inside a tile buffer
+    uint32_t cur_s = smem_u32(tile0), nxt_s = smem_u32(tile1);
+    // neighbours' tiles through distributed shared memory; constant row displacement (see header comment)
+    uint32_t prv_c = 0, prv_n = 0, nex_c = 0, nex_n = 0;
+    if (crank > 0) { prv_c = mapa_u32(cur_s, crank - 1); prv_n = mapa_u32(nxt_s, crank - 1); }
+    if (crank < a.C - 1) { nex_c = mapa_u32(cur_s, crank + 1); nex_n = mapa_u32(nxt_s, crank + 1); }
+    const uint32_t prev_delta = (uint32_t)a.rows_cta * pitchB;      // own row lr -> row R + rows_cta + lr of the previous CTA
+    const uint32_t next_delta = (uint32_t)rows_valid * pitchB;      // own row lr -> row lr - (rows_valid - R) of the next CTA
+    const uint32_t acc_s0 = smem_u32(acc) + (uint32_t)((lr0 - acc_lr0) * wcols + 4 * (qi - a.wq0)) * 4u;
+    const uint32_t accB = (uint32_t)wcols * 4u;
+    const uint32_t sxs_s = smem_u32(sxs) + (uint32_t)lr0 * 4u;
+    const uint32_t inj_s = smem_u32(injb);
+    const bool left_ok = qi > 0, right_ok = qi + 1 < a.nzq;
 
     const int nsteps = a.time_M - a.time_m + 1;
     const int t_first = (MODE == 0) ? a.time_m : a.time_M;
     for (int s = tid; s < ncell; s += blockDim.x) injb[s] = gather(t_first, s);
     cluster.sync();
 
-    float *hist = a.hist ? a.hist + (int64_t)shot * a.hist_shot_stride : nullptr;
-    const int64_t hq = (int64_t)(a.wq1 - a.wq0) * 4;     // history / out row stride
+    // history pointer of this thread's first row at the first time level; advanced by +-one slice per step
+    const int64_t hq = (int64_t)(a.wq1 - a.wq0) * 4;     // history / out row stride (floats)
+    float *hptr = nullptr;
+    if (a.hist)
+        hptr = a.hist + (int64_t)shot * a.hist_shot_stride + (int64_t)(t_first - a.hist_t0) * a.hist_t_stride +
+               (int64_t)(row0 + lr0 - a.wx0) * hq + 4 * (qi - a.wq0);
+    const int64_t hstep = (MODE == 0) ? a.hist_t_stride : -a.hist_t_stride;
+    const float c0 = a.c0, c0_lo = a.c0_lo, inv_dt2 = a.inv_dt2;
+    const bool has_hist = a.hist != nullptr;
 
-    int cur = 0;
     for (int step = 0; step < nsteps; ++step) {
         const int t = (MODE == 0) ? a.time_m + step : a.time_M - step;
-        const float *tc = cur ? tile1 : tile0;
-        float *tn = cur ? tile0 : tile1;
-        float *tprev = cur ? prev0 : prev1;
-        float *tnext = cur ? next0 : next1;
-        const float *injc = injb + (step & 1) * RES2D_MAX_CELLS;
+        const uint32_t injc = inj_s + (uint32_t)(step & 1) * (RES2D_MAX_CELLS * 4u);
         float *injn = injb + ((step + 1) & 1) * RES2D_MAX_CELLS;
 
         // injection values of the NEXT step: loads in flight while this step computes
@@ -160,95 +222,107 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const int off = a.itp_off[4 * (base + i) + c];
-                    if (off >= 0) sum += a.itp_w[4 * (base + i) + c] * tc[off];
+                    if (off >= 0) sum += a.itp_w[4 * (base + i) + c] * lds1(cur_s + (uint32_t)off * 4u);
                 }
                 a.rec[((int64_t)shot * a.nt + t) * a.nrec + a.itp_pt[base + i]] = sum;
             }
         }
 
         if (tactive) {
-            const float *hbase = hist ? hist + (int64_t)(t - a.hist_t0) * a.hist_t_stride : nullptr;
             float4 w[2 * R + 1];
+            uint32_t rw = cur_s + own_off - (uint32_t)R * pitchB;      // window row lr0 - R
 #pragma unroll
-            for (int i = 0; i < 2 * R; i++) w[i] = ld4s(tc + (lr0 + i) * pitch + 4 * qi);
+            for (int i = 0; i < 2 * R; i++) { w[i] = lds4(rw); rw += pitchB; }
+            uint32_t ro = cur_s + own_off;                             // own row, current buffer
+            const uint32_t to_next = nxt_s - cur_s;
+            uint32_t ra = acc_s0;
+            float *hp = hptr;
+            float4 bpre[2] = {z4(), z4()};
+            const float4 *bp = Bp;
+            opaque_ptr(bp);
+            if (vmask & 1u) bpre[0] = __ldg(bp);
+            if (P > 1 && (vmask & 2u)) bpre[1] = __ldg(bp + Bstride);
             // history prefetch (backward): two rows ahead
             float4 hpre[2] = {z4(), z4()};
             if (MODE == 1) {
-#pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const int lr = lr0 + i, row = row0 + lr;
-                    if (i < P && qin && lr < rows_valid && row >= a.wx0 && row < a.wx1)
-                        hpre[i] = __ldg(reinterpret_cast<const float4 *>(hbase + (int64_t)(row - a.wx0) * hq + 4 * (qi - a.wq0)));
-                }
+                if (wmask & 1u) hpre[0] = __ldg(reinterpret_cast<const float4 *>(hp));
+                if (P > 1 && (wmask & 2u)) hpre[1] = __ldg(reinterpret_cast<const float4 *>(hp + hq));
             }
 #pragma unroll
             for (int r = 0; r < P; r++) {
-                const int lr = lr0 + r;
-                w[2 * R] = ld4s(tc + (lr + 2 * R) * pitch + 4 * qi);
+                w[2 * R] = lds4(rw);
+                rw += pitchB;
+                const float4 Bq = bpre[0];
+                bpre[0] = bpre[1];
+                bpre[1] = z4();
+                if (r + 2 < P && (vmask & (1u << ((r + 2) & 31)))) bpre[1] = __ldg(bp + 2 * Bstride);
                 float4 hnow = hpre[0];
                 if (MODE == 1) {
                     hpre[0] = hpre[1];
                     hpre[1] = z4();
-                    const int lr2 = lr + 2, row2 = row0 + lr2;
-                    if (r + 2 < P && qin && lr2 < rows_valid && row2 >= a.wx0 && row2 < a.wx1)
-                        hpre[1] = __ldg(reinterpret_cast<const float4 *>(hbase + (int64_t)(row2 - a.wx0) * hq + 4 * (qi - a.wq0)));
+                    if (r + 2 < P && (wmask & (1u << ((r + 2) & 31)))) hpre[1] = __ldg(reinterpret_cast<const float4 *>(hp + 2 * hq));
                 }
-                if (lr < rows_valid) {
+                if (vmask & (1u << r)) {
                     const float4 Cq = w[R];
-                    const float *crow = tc + (lr + R) * pitch + 4 * qi;
-                    const float4 Lq = (qi > 0) ? ld4s(crow - 4) : z4();
-                    const float4 Rq = (qi + 1 < a.nzq) ? ld4s(crow + 4) : z4();
-                    // Laplacian: centre (hi + lo weight), rows (register window), z (shared neighbours)
-                    float4 lap = fma4s(a.c0, Cq, mul4s(a.c0_lo, Cq));
+                    const float4 Lq = left_ok ? lds4(ro - 16u) : z4();
+                    const float4 Rq = right_ok ? lds4(ro + 16u) : z4();
+                    // Laplacian in two independent chains: centre (hi + lo weight) + rows from the register
+                    // window, and the z neighbours from shared memory
+                    float4 lx = fma4s(c0, Cq, mul4s(c0_lo, Cq));
 #pragma unroll
-                    for (int k = 1; k <= R; k++) lap = fma4s(a.cx[k], add4(w[R + k], w[R - k]), lap);
+                    for (int k = 1; k <= R; k++) lx = fma4s(a.cx[k], add4(w[R + k], w[R - k]), lx);
                     const float zl[12] = {Lq.x, Lq.y, Lq.z, Lq.w, Cq.x, Cq.y, Cq.z, Cq.w, Rq.x, Rq.y, Rq.z, Rq.w};
-                    float2 l01 = lo2(lap), l23 = hi2(lap);
+                    const float2 c1k = make_float2(a.cz[1], a.cz[1]);
+                    float2 l01 = __fmul2_rn(c1k, __fadd2_rn(make_float2(zl[5], zl[6]), make_float2(zl[3], zl[4])));
+                    float2 l23 = __fmul2_rn(c1k, __fadd2_rn(make_float2(zl[7], zl[8]), make_float2(zl[5], zl[6])));
 #pragma unroll
-                    for (int k = 1; k <= R; k++) {
+                    for (int k = 2; k <= R; k++) {
                         const float2 ck = make_float2(a.cz[k], a.cz[k]);
                         l01 = __ffma2_rn(ck, __fadd2_rn(make_float2(zl[4 + k], zl[5 + k]), make_float2(zl[4 - k], zl[5 - k])), l01);
                         l23 = __ffma2_rn(ck, __fadd2_rn(make_float2(zl[6 + k], zl[7 + k]), make_float2(zl[6 - k], zl[7 - k])), l23);
                     }
-                    lap = mk4(l01, l23);
+                    const float4 lap = add4(lx, mk4(l01, l23));
                     // update in increment form
-                    const float4 tmp = fma4(Bq[r], lap, dl[r]);
-                    const float sxr = sxs[lr];
-                    const float4 den = fma4(make_float4(sxr + szq.x, sxr + szq.y, sxr + szq.z, sxr + szq.w), Bq[r],
+                    const float4 tmp = fma4(Bq, lap, dl[r]);
+                    const float sxr = lds1(sxs_s + 4u * r);
+                    const float4 den = fma4(make_float4(sxr + szq.x, sxr + szq.y, sxr + szq.z, sxr + szq.w), Bq,
                                             make_float4(1.f, 1.f, 1.f, 1.f));
                     const float4 c1 = make_float4(rcp_approx(den.x), rcp_approx(den.y), rcp_approx(den.z), rcp_approx(den.w));
                     float4 dn = mul4(c1, tmp);
                     const unsigned rowbits = (unsigned)((imask >> (4 * r)) & 0xFull);
                     if (rowbits) {
                         const unsigned long long below = imask & ((1ull << (4 * r)) - 1ull);
-                        int slot = ibase + __popcll(below);
-                        if (rowbits & 1u) dn.x = fmaf(injc[slot++], Bq[r].x, dn.x);
-                        if (rowbits & 2u) dn.y = fmaf(injc[slot++], Bq[r].y, dn.y);
-                        if (rowbits & 4u) dn.z = fmaf(injc[slot++], Bq[r].z, dn.z);
-                        if (rowbits & 8u) dn.w = fmaf(injc[slot++], Bq[r].w, dn.w);
+                        uint32_t sl = injc + 4u * (uint32_t)(ibase + __popcll(below));
+                        if (rowbits & 1u) { dn.x = fmaf(lds1(sl), Bq.x, dn.x); sl += 4u; }
+                        if (rowbits & 2u) { dn.y = fmaf(lds1(sl), Bq.y, dn.y); sl += 4u; }
+                        if (rowbits & 4u) { dn.z = fmaf(lds1(sl), Bq.z, dn.z); sl += 4u; }
+                        if (rowbits & 8u) { dn.w = fmaf(lds1(sl), Bq.w, dn.w); sl += 4u; }
                     }
                     const float4 un = add4(Cq, dn);
-                    st4s(tn + (lr + R) * pitch + 4 * qi, un);
-                    if (lr < R && tprev) st4s(tprev + (R + a.rows_cta + lr) * pitch + 4 * qi, un);
-                    if (lr >= rows_valid - R && tnext) st4s(tnext + (lr - (rows_valid - R)) * pitch + 4 * qi, un);
-
-                    const int row = row0 + lr;
-                    if (qin && row >= a.wx0 && row < a.wx1) {
-                        float *ap = acc + (lr - acc_lr0) * wcols + 4 * (qi - a.wq0);
+                    sts4(ro + to_next, un);
+                    if (pprev & (1u << r)) sts4_cluster(prv_n + (ro - cur_s) + prev_delta, un);
+                    if (pnext & (1u << r)) sts4_cluster(nex_n + (ro - cur_s) - next_delta, un);
+                    if (wmask & (1u << r)) {
                         if (MODE == 0) {
-                            if (hbase) {
-                                const float4 d2 = mul4s(a.inv_dt2, make_float4(dn.x - dl[r].x, dn.y - dl[r].y,
-                                                                              dn.z - dl[r].z, dn.w - dl[r].w));
-                                st4s(const_cast<float *>(hbase) + (int64_t)(row - a.wx0) * hq + 4 * (qi - a.wq0), d2);
+                            if (has_hist) {
+                                const float4 d2 = mul4s(inv_dt2, make_float4(dn.x - dl[r].x, dn.y - dl[r].y,
+                                                                            dn.z - dl[r].z, dn.w - dl[r].w));
+                                __stcs(reinterpret_cast<float4 *>(hp), d2);       // streaming store: written once, read much later
                             }
-                            if (a.out) st4s(ap, fma4(un, un, ld4s(ap)));            // illum += u[t+1]^2
+                            if (a.out) sts4(ra, fma4(un, un, lds4(ra)));            // illum += u[t+1]^2
                         } else {
                             // grad += -u.dt2[t] * v[t]   (operators.py:217)
-                            st4s(ap, fma4(make_float4(-hnow.x, -hnow.y, -hnow.z, -hnow.w), Cq, ld4s(ap)));
+                            sts4(ra, fma4(make_float4(-hnow.x, -hnow.y, -hnow.z, -hnow.w), Cq, lds4(ra)));
                         }
                     }
                     dl[r] = dn;
                 }
+                ro += pitchB;
+                ra += accB;
+                hp += hq;
+                bp += Bstride;
+                opaque(rw); opaque(ro); opaque(ra);
+                opaque_ptr(hp); opaque_ptr(bp);
 #pragma unroll
                 for (int i = 0; i < 2 * R; i++) w[i] = w[i + 1];
             }
@@ -257,8 +331,12 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
             if (tid < ncell) injn[tid] = injv;
             for (int s = tid + blockDim.x; s < ncell; s += blockDim.x) injn[s] = gather(t_next, s);
         }
-        cluster.sync();
-        cur ^= 1;
+        cluster_barrier();
+        // swap buffers
+        { uint32_t x = cur_s; cur_s = nxt_s; nxt_s = x; }
+        { uint32_t x = prv_c; prv_c = prv_n; prv_n = x; }
+        { uint32_t x = nex_c; nex_c = nex_n; nex_n = x; }
+        if (hptr) hptr += hstep;
     }
 
     // ---- window accumulator -> global
