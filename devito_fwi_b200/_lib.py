@@ -87,6 +87,7 @@ PROTOTYPES = {
     "b2fwi_geometry_mask": (ctypes.c_int, [_G, _I, _P, _I, _P, _P]),
     "b2fwi_crop_mask_accumulate": (ctypes.c_int, [_G, _I, _P, _P, _P, _P]),
     "b2fwi_res2d_plan_model": (ctypes.c_int, [_G, _I, _I, _P]),
+    "b2fwi_res2d_max_active_clusters": (ctypes.c_int, [_G, _P, _P]),
     "b2fwi_res2d_prepare": (ctypes.c_int, [_G, _P, _F, _P, _P]),
     "b2fwi_res2d_forward": (ctypes.c_int, [_G, _P, _P, _P, _P, _F, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P]),
     "b2fwi_res2d_gradient": (ctypes.c_int, [_G, _P, _P, _P, _P, _F, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P]),

@@ -10,6 +10,7 @@ namespace b2fwi {
 
 int launch_res2d(const Res2dArgs &a, int R, int P, int mode, cudaStream_t st);
 size_t res2d_smem_bytes(const Res2dArgs &a, int P);
+int res2d_max_clusters(const Res2dArgs &a, int R, int P, int *out);
 
 static const int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
 
@@ -166,6 +167,18 @@ int b2fwi_res2d_plan_model(const b2fwi_grid *g, int32_t nbl, int32_t min_cluster
     }
     set_error("resident engine: grid %dx%d (space_order %d) does not fit a cluster of <= 8 SMs", nx, nz, g->space_order);
     return B2FWI_EUNSUPPORTED;
+}
+
+int b2fwi_res2d_max_active_clusters(const b2fwi_grid *g, const b2fwi_res2d_plan *plan, int32_t *out)
+{
+    B2_CHECK_ARG(plan && out, "NULL argument");
+    Res2dArgs a;
+    int rc = fill_args(g, plan, &a);
+    if (rc) return rc;
+    int n = 0;
+    rc = res2d_max_clusters(a, g->space_order / 2, plan->rows_per_thread, &n);
+    *out = n;
+    return rc;
 }
 
 int b2fwi_res2d_prepare(const b2fwi_grid *g, const float *vp, float dt, float *B_out, void *stream)

@@ -28,8 +28,6 @@ namespace cg = cooperative_groups;
 namespace b2fwi {
 
 // ---- packed fp32x2 helpers (FFMA2 / FADD2 / FMUL2 on sm_100a)
-static __device__ __forceinline__ float4 ld4s(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-static __device__ __forceinline__ void st4s(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 static __device__ __forceinline__ float4 z4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 static __device__ __forceinline__ float2 lo2(float4 a) { return make_float2(a.x, a.y); }
 static __device__ __forceinline__ float2 hi2(float4 a) { return make_float2(a.z, a.w); }
@@ -92,6 +90,7 @@ static __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+static __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 static __device__ __forceinline__ void cluster_barrier()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -118,7 +117,7 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     const int sc = shot * a.C + crank;
     const int tid = threadIdx.x;
     const int T = a.threads;
-    const int pitch = a.nzq * 4;
+    const int pitch = (a.nzq + 2) * 4;      // one always-zero quad on each side: no edge branches in the z stencil
     const int xg = tid / a.nzq, qi = tid - xg * a.nzq;
     const bool tactive = xg < a.G;
     const int row0 = crank * a.rows_cta;
@@ -143,7 +142,8 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     // delta lives in registers; B = dt^2 vp^2 is re-read from L2 every step with a two-row prefetch
     // (holding it in registers as well spills: 2 x P float4 + the 2R+1-row window exceed the budget)
     float4 dl[P];
-    unsigned vmask = 0, wmask = 0, pprev = 0, pnext = 0;    // per-row flags, bit r
+    // per-row flags, 4 bits per row: 1 valid row, 2 inside the imaging window, 4 push to previous CTA, 8 push to next CTA
+    unsigned long long flags = 0ull;
     const float4 *Bp = reinterpret_cast<const float4 *>(a.B + (int64_t)(row0 + lr0) * a.sr + 4 * qi);
     const int64_t Bstride = a.sr / 4;                        // row stride in float4
 #pragma unroll
@@ -152,10 +152,11 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
         const int lr = lr0 + r, row = row0 + lr;
         const bool ok = tactive && (lr < rows_valid);
         if (ok) {
-            vmask |= 1u << r;
-            if (qi >= a.wq0 && qi < a.wq1 && row >= a.wx0 && row < a.wx1) wmask |= 1u << r;
-            if (lr < R && crank > 0) pprev |= 1u << r;
-            if (lr >= rows_valid - R && crank < a.C - 1) pnext |= 1u << r;
+            unsigned f = 1u;
+            if (qi >= a.wq0 && qi < a.wq1 && row >= a.wx0 && row < a.wx1) f |= 2u;
+            if (lr < R && crank > 0) f |= 4u;
+            if (lr >= rows_valid - R && crank < a.C - 1) f |= 8u;
+            flags |= (unsigned long long)f << (4 * r);
         }
     }
     const float4 szq = tactive ? __ldg(reinterpret_cast<const float4 *>(a.sz + 4 * qi)) : z4();
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
 
     // ---- 32-bit shared addresses (bytes); everything below is an offset from these
     const uint32_t pitchB = (uint32_t)pitch * 4u;
-    const uint32_t own_off = (uint32_t)(lr0 + R) * pitchB + (uint32_t)qi * 16u;     // own row 0 inside a tile buffer
+    const uint32_t own_off = (uint32_t)(lr0 + R) * pitchB + (uint32_t)(qi + 1) * 16u;   // own row 0 inside a tile buffer
     uint32_t cur_s = smem_u32(tile0), nxt_s = smem_u32(tile1);
     // neighbours' tiles through distributed shared memory; constant row displacement (see header comment)
     uint32_t prv_c = 0, prv_n = 0, nex_c = 0, nex_n = 0;
@@ -186,7 +187,6 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     const uint32_t accB = (uint32_t)wcols * 4u;
     const uint32_t sxs_s = smem_u32(sxs) + (uint32_t)lr0 * 4u;
     const uint32_t inj_s = smem_u32(injb);
-    const bool left_ok = qi > 0, right_ok = qi + 1 < a.nzq;
 
     const int nsteps = a.time_M - a.time_m + 1;
     const int t_first = (MODE == 0) ? a.time_m : a.time_M;
@@ -229,48 +229,47 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
         }
 
         if (tactive) {
-            float4 w[2 * R + 1];
-            uint32_t rw = cur_s + own_off - (uint32_t)R * pitchB;      // window row lr0 - R
+            // register window over rows lr-R .. lr+R, addressed circularly with compile-time slots (no moves)
+            constexpr int NW = 2 * R + 1;
+            float4 w[NW];
+            uint32_t rw = cur_s + own_off - (uint32_t)R * pitchB;      // row lr0 - R
 #pragma unroll
             for (int i = 0; i < 2 * R; i++) { w[i] = lds4(rw); rw += pitchB; }
             uint32_t ro = cur_s + own_off;                             // own row, current buffer
-            const uint32_t to_next = nxt_s - cur_s;
+            uint32_t rn = nxt_s + own_off;                             // own row, next buffer
             uint32_t ra = acc_s0;
             float *hp = hptr;
-            float4 bpre[2] = {z4(), z4()};
             const float4 *bp = Bp;
             opaque_ptr(bp);
-            if (vmask & 1u) bpre[0] = __ldg(bp);
-            if (P > 1 && (vmask & 2u)) bpre[1] = __ldg(bp + Bstride);
-            // history prefetch (backward): two rows ahead
-            float4 hpre[2] = {z4(), z4()};
+            float4 bpre[2], hpre[2];
+            if (flags & 0x01ull) bpre[0] = __ldg(bp);
+            if (P > 1 && (flags & 0x10ull)) bpre[1] = __ldg(bp + Bstride);
             if (MODE == 1) {
-                if (wmask & 1u) hpre[0] = __ldg(reinterpret_cast<const float4 *>(hp));
-                if (P > 1 && (wmask & 2u)) hpre[1] = __ldg(reinterpret_cast<const float4 *>(hp + hq));
+                if (flags & 0x02ull) hpre[0] = __ldg(reinterpret_cast<const float4 *>(hp));
+                if (P > 1 && (flags & 0x20ull)) hpre[1] = __ldg(reinterpret_cast<const float4 *>(hp + hq));
             }
 #pragma unroll
             for (int r = 0; r < P; r++) {
-                w[2 * R] = lds4(rw);
+                w[(r + 2 * R) % NW] = lds4(rw);
                 rw += pitchB;
-                const float4 Bq = bpre[0];
-                bpre[0] = bpre[1];
-                bpre[1] = z4();
-                if (r + 2 < P && (vmask & (1u << ((r + 2) & 31)))) bpre[1] = __ldg(bp + 2 * Bstride);
-                float4 hnow = hpre[0];
+                const unsigned f = (unsigned)(flags >> (4 * r)) & 0xFu;
+                const unsigned f2 = (r + 2 < P) ? (unsigned)(flags >> (4 * ((r + 2) & 15))) & 0xFu : 0u;
+                const float4 Bq = bpre[r & 1];
+                if (f2 & 1u) bpre[r & 1] = __ldg(bp + 2 * Bstride);
+                float4 hnow;
                 if (MODE == 1) {
-                    hpre[0] = hpre[1];
-                    hpre[1] = z4();
-                    if (r + 2 < P && (wmask & (1u << ((r + 2) & 31)))) hpre[1] = __ldg(reinterpret_cast<const float4 *>(hp + 2 * hq));
+                    hnow = hpre[r & 1];
+                    if (f2 & 2u) hpre[r & 1] = __ldg(reinterpret_cast<const float4 *>(hp + 2 * hq));
                 }
-                if (vmask & (1u << r)) {
-                    const float4 Cq = w[R];
-                    const float4 Lq = left_ok ? lds4(ro - 16u) : z4();
-                    const float4 Rq = right_ok ? lds4(ro + 16u) : z4();
+                if (f & 1u) {
+                    const float4 Cq = w[(r + R) % NW];
+                    const float4 Lq = lds4(ro - 16u);
+                    const float4 Rq = lds4(ro + 16u);
                     // Laplacian in two independent chains: centre (hi + lo weight) + rows from the register
                     // window, and the z neighbours from shared memory
                     float4 lx = fma4s(c0, Cq, mul4s(c0_lo, Cq));
 #pragma unroll
-                    for (int k = 1; k <= R; k++) lx = fma4s(a.cx[k], add4(w[R + k], w[R - k]), lx);
+                    for (int k = 1; k <= R; k++) lx = fma4s(a.cx[k], add4(w[(r + R + k) % NW], w[(r + R - k + NW) % NW]), lx);
                     const float zl[12] = {Lq.x, Lq.y, Lq.z, Lq.w, Cq.x, Cq.y, Cq.z, Cq.w, Rq.x, Rq.y, Rq.z, Rq.w};
                     const float2 c1k = make_float2(a.cz[1], a.cz[1]);
                     float2 l01 = __fmul2_rn(c1k, __fadd2_rn(make_float2(zl[5], zl[6]), make_float2(zl[3], zl[4])));
@@ -285,8 +284,7 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                     // update in increment form
                     const float4 tmp = fma4(Bq, lap, dl[r]);
                     const float sxr = lds1(sxs_s + 4u * r);
-                    const float4 den = fma4(make_float4(sxr + szq.x, sxr + szq.y, sxr + szq.z, sxr + szq.w), Bq,
-                                            make_float4(1.f, 1.f, 1.f, 1.f));
+                    const float4 den = fma4(add4(make_float4(sxr, sxr, sxr, sxr), szq), Bq, make_float4(1.f, 1.f, 1.f, 1.f));
                     const float4 c1 = make_float4(rcp_approx(den.x), rcp_approx(den.y), rcp_approx(den.z), rcp_approx(den.w));
                     float4 dn = mul4(c1, tmp);
                     const unsigned rowbits = (unsigned)((imask >> (4 * r)) & 0xFull);
@@ -299,15 +297,15 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                         if (rowbits & 8u) { dn.w = fmaf(lds1(sl), Bq.w, dn.w); sl += 4u; }
                     }
                     const float4 un = add4(Cq, dn);
-                    sts4(ro + to_next, un);
-                    if (pprev & (1u << r)) sts4_cluster(prv_n + (ro - cur_s) + prev_delta, un);
-                    if (pnext & (1u << r)) sts4_cluster(nex_n + (ro - cur_s) - next_delta, un);
-                    if (wmask & (1u << r)) {
+                    sts4(rn, un);
+                    if (f & 4u) sts4_cluster(prv_n + (rn - nxt_s) + prev_delta, un);
+                    if (f & 8u) sts4_cluster(nex_n + (rn - nxt_s) - next_delta, un);
+                    if (f & 2u) {
                         if (MODE == 0) {
                             if (has_hist) {
-                                const float4 d2 = mul4s(inv_dt2, make_float4(dn.x - dl[r].x, dn.y - dl[r].y,
-                                                                            dn.z - dl[r].z, dn.w - dl[r].w));
-                                __stcs(reinterpret_cast<float4 *>(hp), d2);       // streaming store: written once, read much later
+                                // u.dt2[t] = (delta+ - delta) / dt^2; streaming store: written once, read much later
+                                const float4 d2 = mul4s(inv_dt2, add4(dn, make_float4(-dl[r].x, -dl[r].y, -dl[r].z, -dl[r].w)));
+                                __stcs(reinterpret_cast<float4 *>(hp), d2);
                             }
                             if (a.out) sts4(ra, fma4(un, un, lds4(ra)));            // illum += u[t+1]^2
                         } else {
@@ -318,13 +316,12 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                     dl[r] = dn;
                 }
                 ro += pitchB;
+                rn += pitchB;
                 ra += accB;
                 hp += hq;
                 bp += Bstride;
-                opaque(rw); opaque(ro); opaque(ra);
+                opaque(rw); opaque(ro); opaque(rn); opaque(ra);
                 opaque_ptr(hp); opaque_ptr(bp);
-#pragma unroll
-                for (int i = 0; i < 2 * R; i++) w[i] = w[i + 1];
             }
         }
         if (more) {
@@ -352,7 +349,7 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
 // ------------------------------------------------------------------------------------------------
 size_t res2d_smem_bytes(const Res2dArgs &a, int P)
 {
-    const size_t pitch = (size_t)a.nzq * 4;
+    const size_t pitch = ((size_t)a.nzq + 2) * 4;
     const size_t wcols = (size_t)(a.wq1 - a.wq0) * 4;
     return sizeof(float) * (2 * (size_t)a.tile_rows * pitch + (size_t)a.rows_cta * wcols + (size_t)a.G * P +
                             2 * RES2D_MAX_CELLS);
@@ -391,6 +388,39 @@ static int launch_P(const Res2dArgs &a, int P, cudaStream_t st)
     case 16: return launch_one<R, 16, MODE>(a, st);
     default: set_error("res2d: unsupported rows-per-thread %d", P); return B2FWI_EUNSUPPORTED;
     }
+}
+
+template <int R, int P>
+static int max_clusters_one(const Res2dArgs &a, int *out)
+{
+    const size_t smem = res2d_smem_bytes(a, P);
+    auto kern = res2d_kernel<R, P, 0>;
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(a.C * 64), 1, 1);
+    cfg.blockDim = dim3((unsigned)a.threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)a.C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2_CUDA(cudaOccupancyMaxActiveClusters(out, kern, &cfg));
+    return 0;
+}
+
+// how many clusters (shots) of this plan the device runs concurrently
+int res2d_max_clusters(const Res2dArgs &a, int R, int P, int *out)
+{
+#define B2_OCASE(r, p) if (R == r && P == p) return max_clusters_one<r, p>(a, out);
+    B2_OCASE(2, 8) B2_OCASE(2, 12) B2_OCASE(2, 16) B2_OCASE(3, 8) B2_OCASE(3, 12) B2_OCASE(3, 16)
+    B2_OCASE(4, 8) B2_OCASE(4, 12) B2_OCASE(4, 16)
+#undef B2_OCASE
+    set_error("res2d: unsupported (R, P) = (%d, %d)", R, P);
+    return B2FWI_EUNSUPPORTED;
 }
 
 int launch_res2d(const Res2dArgs &a, int R, int P, int mode, cudaStream_t st)

@@ -56,7 +56,7 @@ def build_maps(grid, plan, R, inj_coords, itp_coords=None):
     rows_cta = plan.rows_cta
     nzq = (grid.shape[1] + 3) // 4
     gpitch = grid.pitch
-    spitch = nzq * 4
+    spitch = (nzq + 2) * 4            # shared tile row pitch: one zero quad on each side (resident2d.cu)
     nshots = len(inj_coords)
     inj_desc = np.zeros((nshots * C, 2), dtype=np.int32)
     thr_mask = np.zeros((nshots * C, T), dtype=np.uint64)
@@ -129,7 +129,7 @@ def build_maps(grid, plan, R, inj_coords, itp_coords=None):
                 itp_desc[sc] = (sel.size, base)
                 trow = row[sel] - c * rows_cta + R
                 ok = (off[sel] >= 0) & (trow >= 0) & (trow < plan.tile_rows)
-                ioff.append(np.where(ok, trow * spitch + col[sel], -1).astype(np.int32))
+                ioff.append(np.where(ok, trow * spitch + col[sel] + 4, -1).astype(np.int32))
                 iw.append(w[sel].astype(np.float32))
                 ipt.append(sel.astype(np.int32))
                 base += sel.size

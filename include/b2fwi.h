@@ -186,6 +186,10 @@ typedef struct b2fwi_res2d_maps {
  * min_cluster: smallest cluster size to try (1..8). Returns B2FWI_EUNSUPPORTED when nothing fits. */
 int b2fwi_res2d_plan_model(const b2fwi_grid *g, int32_t nbl, int32_t min_cluster, b2fwi_res2d_plan *plan_out);
 
+/* Number of clusters (= shots) of this plan that the current device keeps resident at the same time
+ * (cudaOccupancyMaxActiveClusters); used to pick the cluster size for a given number of shots. */
+int b2fwi_res2d_max_active_clusters(const b2fwi_grid *g, const b2fwi_res2d_plan *plan, int32_t *out);
+
 /* B = dt^2 vp^2 (fp64, rounded once) as a pitched slice. */
 int b2fwi_res2d_prepare(const b2fwi_grid *g, const float *vp, float dt, float *B_out, void *stream);
 
