@@ -357,15 +357,21 @@ def fwi_obj_multi(geometry, obs, misfit_func, direct_wave=None, mask=None, preco
     else:
         buf[2 * n] = float(fval)
     dist.all_reduce_sum(buf)
-    host = buf.cpu().numpy()
+    return _finalize_objective(buf.cpu().numpy(), model.shape, mask, precond, calc_grad) + (residuals,)
+
+
+def _finalize_objective(host, shape, mask, precond, calc_grad):
+    """[grad | illum | fval] summed over shots and ranks -> (fval, grad): illumination preconditioning
+    and bathymetry mask of fwi.py:200-204, applied identically (and redundantly) on every rank."""
+    n = int(np.prod(shape))
     fval = float(host[2 * n])
-    grad = host[:n].reshape(model.shape).copy()
+    grad = host[:n].reshape(shape).copy()
     if calc_grad:
         if precond:
-            grad /= np.sqrt(host[n:2 * n].reshape(model.shape) + 1e-30)
+            grad /= np.sqrt(host[n:2 * n].reshape(shape) + 1e-30)
         if mask is not None:
             grad *= mask
-    return fval, grad.reshape(-1).astype(np.float64), residuals
+    return fval, grad.reshape(-1).astype(np.float64)
 
 
 def fwi_loss(x, geometry, obs, misfit_func, direct_wave=None, mask=None, precond=True, calc_grad=True):
