@@ -186,6 +186,9 @@ def run_b200(args):
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     work = 2.0 * npts * steps_per_sweep * nshots_job            # forward + adjoint grid-point-steps per step

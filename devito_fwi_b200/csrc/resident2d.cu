@@ -21,45 +21,12 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "packed.cuh"
 #include "resident2d.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace b2fwi {
-
-// ---- packed fp32x2 helpers (FFMA2 / FADD2 / FMUL2 on sm_100a)
-static __device__ __forceinline__ float4 z4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-static __device__ __forceinline__ float2 lo2(float4 a) { return make_float2(a.x, a.y); }
-static __device__ __forceinline__ float2 hi2(float4 a) { return make_float2(a.z, a.w); }
-static __device__ __forceinline__ float4 mk4(float2 l, float2 h) { return make_float4(l.x, l.y, h.x, h.y); }
-static __device__ __forceinline__ float4 add4(float4 a, float4 b)
-{
-    return mk4(__fadd2_rn(lo2(a), lo2(b)), __fadd2_rn(hi2(a), hi2(b)));
-}
-static __device__ __forceinline__ float4 fma4s(float s, float4 a, float4 c)   // s*a + c
-{
-    const float2 ss = make_float2(s, s);
-    return mk4(__ffma2_rn(ss, lo2(a), lo2(c)), __ffma2_rn(ss, hi2(a), hi2(c)));
-}
-static __device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c)   // a*b + c
-{
-    return mk4(__ffma2_rn(lo2(a), lo2(b), lo2(c)), __ffma2_rn(hi2(a), hi2(b), hi2(c)));
-}
-static __device__ __forceinline__ float4 mul4(float4 a, float4 b)
-{
-    return mk4(__fmul2_rn(lo2(a), lo2(b)), __fmul2_rn(hi2(a), hi2(b)));
-}
-static __device__ __forceinline__ float4 mul4s(float s, float4 a)
-{
-    const float2 ss = make_float2(s, s);
-    return mk4(__fmul2_rn(ss, lo2(a)), __fmul2_rn(ss, hi2(a)));
-}
-static __device__ __forceinline__ float rcp_approx(float x)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 
 // ---- raw shared / distributed-shared accessors on 32-bit addresses (no generic-address arithmetic in the hot loop)
 static __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,7 +57,6 @@ static __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
-static __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 static __device__ __forceinline__ void cluster_barrier()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -263,6 +229,10 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                 }
                 if (f & 1u) {
                     const float4 Cq = w[(r + R) % NW];
+                    if (MODE == 1 && (f & 2u)) {
+                        // grad += -u.dt2[t] * v[t]   (operators.py:217); done first so the history registers die early
+                        sts4(ra, fma4(make_float4(-hnow.x, -hnow.y, -hnow.z, -hnow.w), Cq, lds4(ra)));
+                    }
                     const float4 Lq = lds4(ro - 16u);
                     const float4 Rq = lds4(ro + 16u);
                     // Laplacian in two independent chains: centre (hi + lo weight) + rows from the register
@@ -300,17 +270,14 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                     sts4(rn, un);
                     if (f & 4u) sts4_cluster(prv_n + (rn - nxt_s) + prev_delta, un);
                     if (f & 8u) sts4_cluster(nex_n + (rn - nxt_s) - next_delta, un);
-                    if (f & 2u) {
-                        if (MODE == 0) {
+                    if (MODE == 0 && (f & 2u)) {
+                        {
                             if (has_hist) {
                                 // u.dt2[t] = (delta+ - delta) / dt^2; streaming store: written once, read much later
                                 const float4 d2 = mul4s(inv_dt2, add4(dn, make_float4(-dl[r].x, -dl[r].y, -dl[r].z, -dl[r].w)));
                                 __stcs(reinterpret_cast<float4 *>(hp), d2);
                             }
                             if (a.out) sts4(ra, fma4(un, un, lds4(ra)));            // illum += u[t+1]^2
-                        } else {
-                            // grad += -u.dt2[t] * v[t]   (operators.py:217)
-                            sts4(ra, fma4(make_float4(-hnow.x, -hnow.y, -hnow.z, -hnow.w), Cq, lds4(ra)));
                         }
                     }
                     dl[r] = dn;

@@ -11,7 +11,10 @@
 // plane's halo and pipeline head are prefetched into registers while the current plane computes.
 // The same kernel fuses, per point: the OT2 update, the zero-lag imaging condition
 // (grad -= u.dt2 * v), the source-illumination accumulation and the u.dt2 history store.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "packed.cuh"
 #include "stream_kernels.cuh"
 
 namespace b2fwi {
@@ -27,8 +30,68 @@ static __device__ __forceinline__ float d2u_of(float um, float uc, float up, flo
     return __fmul_rn(__fadd_rn(__fmaf_rn(-2.f, uc, um), up), inv_dt2);
 }
 
-template <int R, int NDIM, int IMG>
-__global__ void __launch_bounds__(256, 2) step_kernel(const __grid_constant__ StepArgs a)
+// The point update shared by all streaming kernels (identical arithmetic => identical results whichever
+// kernel variant computes a sweep): packed fp32x2, three independent accumulation chains.
+//   q[0..NQ-1]: register pipeline along the plane axis (centre at QC); ctr: this thread's float4 in the staged tile.
+//   The pipeline is addressed circularly: plane offset i in -R..R lives in q[(j + R + i) % NQ] (j: rotation).
+template <int R, int NDIM, int SW>
+static __device__ __forceinline__ float4 point_update(const StepArgs &a, const float4 *q, int j, const float *ctr,
+                                                     float4 prev, float4 c1, float4 c2, int z0)
+{
+    constexpr int RZ4 = (R + 3) / 4, ZH = 4 * RZ4;
+    constexpr int NQ = (NDIM == 3) ? 2 * R + 1 : 1;
+    constexpr int QC = (NDIM == 3) ? R : 0;
+    const float4 C = q[(j + QC) % NQ];
+    float4 lp = fma4s(a.c0, C, mul4s(a.c0_lo, C));          // centre weight as exact hi + lo (see api.cu)
+    if (NDIM == 3) {
+#pragma unroll
+        for (int k = 1; k <= R; k++) lp = fma4s(a.cp[k], add4(q[(j + QC + k) % NQ], q[(j + QC - k + NQ) % NQ]), lp);
+    }
+    float4 lr = mul4s(a.cr[1], add4(ld4(ctr + SW), ld4(ctr - SW)));
+#pragma unroll
+    for (int k = 2; k <= R; k++) lr = fma4s(a.cr[k], add4(ld4(ctr + k * SW), ld4(ctr - k * SW)), lr);
+    float zl[ZH + 4 + ZH];
+#pragma unroll
+    for (int i = 0; i < RZ4; i++) {
+        const float4 Lq = ld4(ctr - ZH + 4 * i), Rq = ld4(ctr + 4 + 4 * i);
+        zl[4 * i + 0] = Lq.x; zl[4 * i + 1] = Lq.y; zl[4 * i + 2] = Lq.z; zl[4 * i + 3] = Lq.w;
+        zl[ZH + 4 + 4 * i + 0] = Rq.x; zl[ZH + 4 + 4 * i + 1] = Rq.y;
+        zl[ZH + 4 + 4 * i + 2] = Rq.z; zl[ZH + 4 + 4 * i + 3] = Rq.w;
+    }
+    zl[ZH + 0] = C.x; zl[ZH + 1] = C.y; zl[ZH + 2] = C.z; zl[ZH + 3] = C.w;
+    const float2 c1k = make_float2(a.cz[1], a.cz[1]);
+    float2 l01 = __fmul2_rn(c1k, __fadd2_rn(make_float2(zl[ZH + 1], zl[ZH + 2]), make_float2(zl[ZH - 1], zl[ZH])));
+    float2 l23 = __fmul2_rn(c1k, __fadd2_rn(make_float2(zl[ZH + 3], zl[ZH + 4]), make_float2(zl[ZH + 1], zl[ZH + 2])));
+#pragma unroll
+    for (int k = 2; k <= R; k++) {
+        const float2 ck = make_float2(a.cz[k], a.cz[k]);
+        l01 = __ffma2_rn(ck, __fadd2_rn(make_float2(zl[ZH + k], zl[ZH + 1 + k]), make_float2(zl[ZH - k], zl[ZH + 1 - k])), l01);
+        l23 = __ffma2_rn(ck, __fadd2_rn(make_float2(zl[ZH + 2 + k], zl[ZH + 3 + k]),
+                                        make_float2(zl[ZH + 2 - k], zl[ZH + 3 - k])), l23);
+    }
+    const float4 lap = add4(add4(lp, lr), mk4(l01, l23));
+    // u+ = u + c1 (u - u-) + c2 L(u)
+    const float4 t = fma4(c1, add4(C, make_float4(-prev.x, -prev.y, -prev.z, -prev.w)), C);
+    float4 o = fma4(c2, lap, t);
+    if (z0 + 1 >= a.nz) o.y = 0.f;
+    if (z0 + 2 >= a.nz) o.z = 0.f;
+    if (z0 + 3 >= a.nz) o.w = 0.f;
+    return o;
+}
+
+static __device__ __forceinline__ float4 d2u4(float4 um, float4 uc, float4 up, float inv_dt2)
+{
+    return make_float4(d2u_of(um.x, uc.x, up.x, inv_dt2), d2u_of(um.y, uc.y, up.y, inv_dt2),
+                       d2u_of(um.z, uc.z, up.z, inv_dt2), d2u_of(um.w, uc.w, up.w, inv_dt2));
+}
+static __device__ __forceinline__ float4 img4(float4 g, float4 d2, float4 v)     // grad += -u.dt2 * v
+{
+    return make_float4(__fmaf_rn(-d2.x, v.x, g.x), __fmaf_rn(-d2.y, v.y, g.y), __fmaf_rn(-d2.z, v.z, g.z),
+                       __fmaf_rn(-d2.w, v.w, g.w));
+}
+
+template <int R, int NDIM, int IMG, int MINB>
+__global__ void __launch_bounds__(256, MINB) step_kernel(const __grid_constant__ StepArgs a)
 {
     constexpr int TR = 16;                 // rows per tile
     constexpr int RZ4 = (R + 3) / 4;       // z-halo width in float4
@@ -95,144 +158,248 @@ __global__ void __launch_bounds__(256, 2) step_kernel(const __grid_constant__ St
     for (int i = 0; i < NH; i++)
         hreg[i] = (hoff[i] >= 0) ? ld4(a.cur + hoff[i] + (int64_t)p_begin * (NDIM == 3 ? a.sp : 0)) : zero4();
 
-    for (int p = p_begin; p < p_end; ++p) {
-        const int buf = (p - p_begin) & 1;
-        float *tb = &tile[buf][0][0];
-        const int64_t pofs = (NDIM == 3) ? (int64_t)p * a.sp : 0;
-        // stage plane p
-        st4(tb + (R + tr) * SW + ZH + 4 * tz, q[QC]);
+    // plane loop; for R <= 4 it is unrolled NQ times so that the register pipeline rotates through
+    // compile-time slots instead of being shifted (2R float4 moves per plane otherwise)
+    constexpr int UNR = (NDIM == 3 && R <= 4) ? NQ : 1;
+    for (int pb = p_begin; pb < p_end; pb += UNR) {
 #pragma unroll
-        for (int i = 0; i < NH; i++)
-            if (hsm[i] >= 0) st4(tb + hsm[i], hreg[i]);
+        for (int j = 0; j < UNR; j++) {
+            const int p = pb + j;
+            if (p < p_end) {
+                const int buf = (p - p_begin) & 1;
+                float *tb = &tile[buf][0][0];
+                const int64_t pofs = (NDIM == 3) ? (int64_t)p * a.sp : 0;
+                // stage plane p
+                st4(tb + (R + tr) * SW + ZH + 4 * tz, q[(j + QC) % NQ]);
+#pragma unroll
+                for (int i = 0; i < NH; i++)
+                    if (hsm[i] >= 0) st4(tb + hsm[i], hreg[i]);
 
-        // pointwise operands of plane p
-        float4 prev = zero4(), c1 = zero4(), c2 = zero4();
-        float4 g4 = zero4(), h0 = zero4(), h1 = zero4(), h2 = zero4(), il = zero4();
-        if (active) {
-            prev = ld4(a.prev + own0 + pofs);
-            c1 = ldg4(a.c1 + own0 + pofs);
-            c2 = ldg4(a.c2 + own0 + pofs);
-            if (IMG != 0) {
-                g4 = ld4(a.grad + own0 + pofs);
-                h1 = ldg4(a.h1 + own0 + pofs);
-                if (IMG == 1) {
-                    h0 = ldg4(a.h0 + own0 + pofs);
-                    h2 = ldg4(a.h2 + own0 + pofs);
+                // pointwise operands of plane p
+                float4 prev = zero4(), c1 = zero4(), c2 = zero4();
+                float4 g4 = zero4(), h0 = zero4(), h1 = zero4(), h2 = zero4(), il = zero4();
+                if (active) {
+                    prev = ld4(a.prev + own0 + pofs);
+                    c1 = ldg4(a.c1 + own0 + pofs);
+                    c2 = ldg4(a.c2 + own0 + pofs);
+                    if (IMG != 0) {
+                        g4 = ld4(a.grad + own0 + pofs);
+                        h1 = ldg4(a.h1 + own0 + pofs);
+                        if (IMG == 1) {
+                            h0 = ldg4(a.h0 + own0 + pofs);
+                            h2 = ldg4(a.h2 + own0 + pofs);
+                        }
+                    }
+                    if (a.illum) il = ld4(a.illum + own0 + pofs);
+                }
+                // prefetch for plane p+1
+                float4 qn = zero4();
+                if (p + 1 < p_end) {
+                    if (NDIM == 3) {
+                        const int pn = p + R + 1;
+                        if (active && pn < a.np) qn = ld4(a.cur + own0 + (int64_t)pn * a.sp);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NH; i++)
+                        hreg[i] = (hoff[i] >= 0) ? ld4(a.cur + hoff[i] + pofs + a.sp) : zero4();
+                }
+                __syncthreads();
+
+                if (active) {
+                    const float4 C = q[(j + QC) % NQ];
+                    const float4 o = point_update<R, NDIM, SW>(a, q, j, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, z0);
+                    st4(a.out + own0 + pofs, o);
+                    if (IMG != 0) st4(a.grad + own0 + pofs, img4(g4, IMG == 1 ? d2u4(h0, h1, h2, a.inv_dt2) : h1, C));
+                    if (a.illum) st4(a.illum + own0 + pofs, fma4(C, C, il));
+                    if (a.d2u) {
+                        float4 d = d2u4(prev, C, o, a.inv_dt2);
+                        if (z0 + 1 >= a.nz) d.y = 0.f;
+                        if (z0 + 2 >= a.nz) d.z = 0.f;
+                        if (z0 + 3 >= a.nz) d.w = 0.f;
+                        st4(a.d2u + own0 + pofs, d);
+                    }
+                }
+                if (NDIM == 3) {
+                    if (UNR == NQ) {
+                        q[j % NQ] = qn;                     // the oldest plane's slot receives plane p+R+1
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NQ - 1; i++) q[i] = q[i + 1];
+                        q[NQ - 1] = qn;
+                    }
                 }
             }
-            if (a.illum) il = ld4(a.illum + own0 + pofs);
-        }
-        // prefetch for plane p+1
-        float4 qn = zero4();
-        if (p + 1 < p_end) {
-            if (NDIM == 3) {
-                const int pn = p + R + 1;
-                if (active && pn < a.np) qn = ld4(a.cur + own0 + (int64_t)pn * a.sp);
-            }
-#pragma unroll
-            for (int i = 0; i < NH; i++)
-                hreg[i] = (hoff[i] >= 0) ? ld4(a.cur + hoff[i] + pofs + a.sp) : zero4();
-        }
-        __syncthreads();
-
-        if (active) {
-            const float4 C = q[QC];
-            float lap[4] = {fmaf(a.c0, C.x, a.c0_lo * C.x), fmaf(a.c0, C.y, a.c0_lo * C.y),
-                            fmaf(a.c0, C.z, a.c0_lo * C.z), fmaf(a.c0, C.w, a.c0_lo * C.w)};
-            if (NDIM == 3) {
-#pragma unroll
-                for (int k = 1; k <= R; k++) {
-                    const float4 A = q[QC + k], B = q[QC - k];
-                    const float c = a.cp[k];
-                    lap[0] = fmaf(c, A.x + B.x, lap[0]);
-                    lap[1] = fmaf(c, A.y + B.y, lap[1]);
-                    lap[2] = fmaf(c, A.z + B.z, lap[2]);
-                    lap[3] = fmaf(c, A.w + B.w, lap[3]);
-                }
-            }
-            const float *ctr = tb + (R + tr) * SW + ZH + 4 * tz;
-#pragma unroll
-            for (int k = 1; k <= R; k++) {
-                const float4 A = ld4(ctr + k * SW), B = ld4(ctr - k * SW);
-                const float c = a.cr[k];
-                lap[0] = fmaf(c, A.x + B.x, lap[0]);
-                lap[1] = fmaf(c, A.y + B.y, lap[1]);
-                lap[2] = fmaf(c, A.z + B.z, lap[2]);
-                lap[3] = fmaf(c, A.w + B.w, lap[3]);
-            }
-            float zl[ZH + 4 + ZH];
-#pragma unroll
-            for (int i = 0; i < RZ4; i++) {
-                const float4 Lq = ld4(ctr - ZH + 4 * i), Rq = ld4(ctr + 4 + 4 * i);
-                zl[4 * i + 0] = Lq.x; zl[4 * i + 1] = Lq.y; zl[4 * i + 2] = Lq.z; zl[4 * i + 3] = Lq.w;
-                zl[ZH + 4 + 4 * i + 0] = Rq.x; zl[ZH + 4 + 4 * i + 1] = Rq.y;
-                zl[ZH + 4 + 4 * i + 2] = Rq.z; zl[ZH + 4 + 4 * i + 3] = Rq.w;
-            }
-            zl[ZH + 0] = C.x; zl[ZH + 1] = C.y; zl[ZH + 2] = C.z; zl[ZH + 3] = C.w;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-#pragma unroll
-                for (int k = 1; k <= R; k++)
-                    lap[j] = fmaf(a.cz[k], zl[ZH + j + k] + zl[ZH + j - k], lap[j]);
-
-            float o[4];
-            const float Cv[4] = {C.x, C.y, C.z, C.w};
-            const float Pv[4] = {prev.x, prev.y, prev.z, prev.w};
-            const float c1v[4] = {c1.x, c1.y, c1.z, c1.w};
-            const float c2v[4] = {c2.x, c2.y, c2.z, c2.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float t = fmaf(c1v[j], Cv[j] - Pv[j], Cv[j]);
-                o[j] = (z0 + j < a.nz) ? fmaf(c2v[j], lap[j], t) : 0.f;
-            }
-            st4(a.out + own0 + pofs, make_float4(o[0], o[1], o[2], o[3]));
-
-            if (IMG != 0) {
-                float d2[4];
-                if (IMG == 1) {
-                    d2[0] = d2u_of(h0.x, h1.x, h2.x, a.inv_dt2);
-                    d2[1] = d2u_of(h0.y, h1.y, h2.y, a.inv_dt2);
-                    d2[2] = d2u_of(h0.z, h1.z, h2.z, a.inv_dt2);
-                    d2[3] = d2u_of(h0.w, h1.w, h2.w, a.inv_dt2);
-                } else {
-                    d2[0] = h1.x; d2[1] = h1.y; d2[2] = h1.z; d2[3] = h1.w;
-                }
-                g4.x = __fmaf_rn(-d2[0], C.x, g4.x);
-                g4.y = __fmaf_rn(-d2[1], C.y, g4.y);
-                g4.z = __fmaf_rn(-d2[2], C.z, g4.z);
-                g4.w = __fmaf_rn(-d2[3], C.w, g4.w);
-                st4(a.grad + own0 + pofs, g4);
-            }
-            if (a.illum) {
-                il.x = fmaf(C.x, C.x, il.x); il.y = fmaf(C.y, C.y, il.y);
-                il.z = fmaf(C.z, C.z, il.z); il.w = fmaf(C.w, C.w, il.w);
-                st4(a.illum + own0 + pofs, il);
-            }
-            if (a.d2u) {
-                float4 d;
-                d.x = (z0 + 0 < a.nz) ? d2u_of(prev.x, C.x, o[0], a.inv_dt2) : 0.f;
-                d.y = (z0 + 1 < a.nz) ? d2u_of(prev.y, C.y, o[1], a.inv_dt2) : 0.f;
-                d.z = (z0 + 2 < a.nz) ? d2u_of(prev.z, C.z, o[2], a.inv_dt2) : 0.f;
-                d.w = (z0 + 3 < a.nz) ? d2u_of(prev.w, C.w, o[3], a.inv_dt2) : 0.f;
-                st4(a.d2u + own0 + pofs, d);
-            }
-        }
-        if (NDIM == 3) {
-#pragma unroll
-            for (int i = 0; i < NQ - 1; i++) q[i] = q[i + 1];
-            q[NQ - 1] = qn;
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// 3-D variant with an asynchronous-copy pipeline (cp.async, three stages): the halo of plane p+2 goes
+// straight into the shared tile ring and the pointwise operands (u[t-1], the two coefficients and, for the
+// imaging sweep, grad and u.dt2) of plane p+2 into thread-private shared slots while plane p computes, so no
+// HBM latency sits between the per-plane barrier and the arithmetic. IMG: 0 forward, 2 imaging from u.dt2.
+static __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid)
+{
+    const int sz = valid ? 16 : 0;        // src-size 0: 16 bytes of zeros are written, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int R, int IMG>
+__global__ void __launch_bounds__(256, 2) step3d_async_kernel(const __grid_constant__ StepArgs a)
+{
+    constexpr int TR = 16, RZ4 = (R + 3) / 4, ZH = 4 * RZ4, SW = 64 + 2 * ZH, SROWS = TR + 2 * R;
+    constexpr int NHALO = 2 * R * 16 + TR * 2 * RZ4, NH = (NHALO + 255) / 256;
+    constexpr int NQ = 2 * R + 1, QC = R;
+    constexpr int NB = 3;                               // pipeline stages
+    constexpr int NAUX = (IMG == 2) ? 5 : 3;            // prev, c1, c2 [, grad, u.dt2]
+
+    extern __shared__ __align__(16) float dsm[];
+    float *tiles = dsm;                                               // [NB][SROWS][SW]
+    float4 *aux = reinterpret_cast<float4 *>(dsm + NB * SROWS * SW);  // [NB][NAUX][256], thread-private slots
+
+    const int tz = threadIdx.x, tr = threadIdx.y, tid = tr * 16 + tz;
+    const int ztile0 = blockIdx.x * 64;
+    const int z0 = ztile0 + tz * 4;
+    const int r0 = blockIdx.y * TR;
+    const int r = r0 + tr;
+    const bool active = (r < a.nr) && (z0 < a.nz);
+    const int p_begin = (int)blockIdx.z * a.chunk;
+    const int p_end = min(p_begin + a.chunk, a.np);
+    const int64_t H = a.halo;
+    const int64_t own0 = H * a.sp + (int64_t)(r + H) * a.sr + (z0 + H);
+    const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(tiles);
+    const uint32_t aux_s = (uint32_t)__cvta_generic_to_shared(aux);
+
+    int64_t hoff[NH];
+    int hsm[NH];
+#pragma unroll
+    for (int i = 0; i < NH; i++) {
+        const int h = tid + i * 256;
+        int srow = -1, scol = 0, gz = 0;
+        if (h < 2 * R * 16) {
+            const int hr = h >> 4, hz = h & 15;
+            srow = (hr < R) ? hr : hr + TR;
+            scol = ZH + 4 * hz;
+            gz = ztile0 + 4 * hz;
+        } else if (h < NHALO) {
+            const int j = h - 2 * R * 16;
+            const int row = j / (2 * RZ4), c = j % (2 * RZ4);
+            srow = R + row;
+            if (c < RZ4) { scol = 4 * c; gz = ztile0 - ZH + 4 * c; }
+            else { scol = ZH + 64 + 4 * (c - RZ4); gz = ztile0 + 64 + 4 * (c - RZ4); }
+        }
+        hsm[i] = (srow >= 0) ? srow * SW + scol : -1;
+        const int gr = r0 - R + srow;
+        const bool ok = (srow >= 0) && gr >= 0 && gr < a.nr && gz >= 0 && gz < a.nz;
+        hoff[i] = ok ? H * a.sp + (int64_t)(gr + H) * a.sr + (gz + H) : -1;
+    }
+
+    auto issue = [&](int p) {
+        if (p < p_end) {
+            const int slot = (p - p_begin) % NB;
+            const int64_t pofs = (int64_t)p * a.sp;
+#pragma unroll
+            for (int i = 0; i < NH; i++)
+                if (hsm[i] >= 0)
+                    cp_async16(tiles_s + (uint32_t)(slot * SROWS * SW + hsm[i]) * 4u,
+                               a.cur + (hoff[i] >= 0 ? hoff[i] + pofs : 0), hoff[i] >= 0);
+            const uint32_t d = aux_s + (uint32_t)((slot * NAUX) * 256 + tid) * 16u;
+            const int64_t o = active ? own0 + pofs : 0;
+            cp_async16(d, a.prev + o, active);
+            cp_async16(d + 256u * 16u, a.c1 + o, active);
+            cp_async16(d + 2u * 256u * 16u, a.c2 + o, active);
+            if (IMG == 2) {
+                cp_async16(d + 3u * 256u * 16u, a.grad + o, active);
+                cp_async16(d + 4u * 256u * 16u, a.h1 + o, active);
+            }
+        }
+        cp_async_commit();      // one group per plane, possibly empty: keeps the wait count uniform
+    };
+
+    float4 q[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; i++) {
+        const int p = p_begin - R + i;
+        q[i] = (active && p >= 0 && p < a.np) ? ld4(a.cur + own0 + (int64_t)p * a.sp) : zero4();
+    }
+    issue(p_begin);
+    issue(p_begin + 1);
+
+    for (int p = p_begin; p < p_end; ++p) {
+        const int slot = (p - p_begin) % NB;
+        float *tb = tiles + slot * SROWS * SW;
+        const int64_t pofs = (int64_t)p * a.sp;
+        st4(tb + (R + tr) * SW + ZH + 4 * tz, q[QC]);
+        cp_async_wait<1>();         // this thread's copies for plane p have landed (plane p+1 may be in flight)
+        __syncthreads();
+        issue(p + 2);               // ring slot (p+2)%3 == slot of plane p-1, whose readers all passed the barrier
+        float4 qn = zero4();
+        const int pn = p + R + 1;
+        if (p + 1 < p_end && active && pn < a.np) qn = ld4(a.cur + own0 + (int64_t)pn * a.sp);
+        float4 il = zero4();
+        if (a.illum && active) il = ld4(a.illum + own0 + pofs);
+
+        if (active) {
+            const float4 *ax = aux + (slot * NAUX) * 256 + tid;
+            const float4 prev = ax[0], c1 = ax[256], c2 = ax[512];
+            const float4 C = q[QC];
+            const float4 o = point_update<R, 3, SW>(a, q, 0, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, z0);
+            st4(a.out + own0 + pofs, o);
+            if (IMG == 2) st4(a.grad + own0 + pofs, img4(ax[768], ax[1024], C));
+            if (a.illum) st4(a.illum + own0 + pofs, fma4(C, C, il));
+            if (a.d2u) {
+                float4 d = d2u4(prev, C, o, a.inv_dt2);
+                if (z0 + 1 >= a.nz) d.y = 0.f;
+                if (z0 + 2 >= a.nz) d.z = 0.f;
+                if (z0 + 3 >= a.nz) d.w = 0.f;
+                st4(a.d2u + own0 + pofs, d);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NQ - 1; i++) q[i] = q[i + 1];
+        q[NQ - 1] = qn;
+    }
+    cp_async_wait<0>();
+}
+
+template <int R, int IMG>
+static int launch_async(const StepArgs &a, dim3 grid, cudaStream_t st)
+{
+    constexpr int RZ4 = (R + 3) / 4, SW = 64 + 8 * RZ4, SROWS = 16 + 2 * R, NAUX = (IMG == 2) ? 5 : 3;
+    const size_t smem = (size_t)3 * SROWS * SW * 4 + (size_t)3 * NAUX * 256 * 16;
+    auto kern = step3d_async_kernel<R, IMG>;
+    static bool configured = false;
+    if (!configured) {
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    kern<<<grid, dim3(16, 16, 1), smem, st>>>(a);
+    B2_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+static const int g_minb = []() { const char *e = getenv("B2FWI_MINB"); return e ? atoi(e) : 2; }();
+static const int g_async = []() { const char *e = getenv("B2FWI_ASYNC_KERNEL"); return e ? atoi(e) : -1; }();   // -1: auto
 
 template <int R, int NDIM>
 static int launch_step_img(const Layout &L, const StepArgs &a, int img, dim3 grid, cudaStream_t st)
 {
     dim3 block(16, 16, 1);
+    const bool three = (NDIM == 3) && g_minb == 3 && R <= 4;
     switch (img) {
-    case 0: step_kernel<R, NDIM, 0><<<grid, block, 0, st>>>(a); break;
-    case 1: step_kernel<R, NDIM, 1><<<grid, block, 0, st>>>(a); break;
-    case 2: step_kernel<R, NDIM, 2><<<grid, block, 0, st>>>(a); break;
+    case 0:
+        if (three) step_kernel<R, NDIM, 0, (R <= 4 ? 3 : 2)><<<grid, block, 0, st>>>(a);
+        else step_kernel<R, NDIM, 0, 2><<<grid, block, 0, st>>>(a);
+        break;
+    case 1: step_kernel<R, NDIM, 1, 2><<<grid, block, 0, st>>>(a); break;
+    case 2:
+        if (three) step_kernel<R, NDIM, 2, (R <= 4 ? 3 : 2)><<<grid, block, 0, st>>>(a);
+        else step_kernel<R, NDIM, 2, 2><<<grid, block, 0, st>>>(a);
+        break;
     default: set_error("bad imaging mode %d", img); return B2FWI_EINVAL;
     }
     B2_CUDA(cudaGetLastError());
@@ -250,7 +417,7 @@ int pick_chunk(const Layout &L)
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess)
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        n_slots = 2 * sms;
+        n_slots = g_minb * sms;
     }
     const long tiles = (long)((L.nz + 63) / 64) * ((L.nr + 15) / 16);
     int best_nc = 1;
@@ -267,6 +434,11 @@ int pick_chunk(const Layout &L)
     return (L.np + best_nc - 1) / best_nc;
 }
 
+// Kernel choice for 3-D sweeps, measured on 592^3 (fraction of the 6.46 TB/s copy bandwidth, forward sweep):
+//   so <= 8 : register-staged kernel 0.71 vs cp.async pipeline 0.67;  so = 16: cp.async pipeline 0.61 vs 0.50.
+// B2FWI_ASYNC_KERNEL=0/1 overrides for A/B comparison.
+static bool use_async(int R) { return g_async < 0 ? R > 4 : g_async == 1; }
+
 int launch_step(const Layout &L, StepArgs a, int img, cudaStream_t st)
 {
     a.np = L.np; a.nr = L.nr; a.nz = L.nz; a.halo = L.halo; a.sp = L.sp; a.sr = L.sr;
@@ -275,6 +447,8 @@ int launch_step(const Layout &L, StepArgs a, int img, cudaStream_t st)
     dim3 grid((L.nz + 63) / 64, (L.nr + 15) / 16, nchunks);
 #define B2_CASE(r)                                                              \
     case r:                                                                     \
+        if (L.ndim == 3 && img == 0 && use_async(r)) return launch_async<r, 0>(a, grid, st);   \
+        if (L.ndim == 3 && img == 2 && use_async(r)) return launch_async<r, 2>(a, grid, st);   \
         return (L.ndim == 3) ? launch_step_img<r, 3>(L, a, img, grid, st)       \
                              : launch_step_img<r, 2>(L, a, img, grid, st);
     switch (L.R) {
