@@ -219,13 +219,20 @@ def run_b200(args):
     }
     if kern:
         dom = max(kern, key=lambda k: kern[k]["ms_per_launch"])
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = int(json.load(f)[dom]["dram_bytes"])      # per launch, from the committed ncu capture
+        except Exception:
+            pass
         out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved"], "peak": peak,
-                           "unit": "GB/s", "frac": round(kern[dom]["achieved"] / peak, 3), "traffic": None,
+                           "unit": "GB/s", "frac": round(kern[dom]["achieved"] / peak, 3), "traffic": traffic,
                            "peak_source": peak_src,
-                           "note": "algorithmic bytes (20 B fwd / 32 B adj+img per grid-point-step) over the live "
-                                   "CUDA-event duration; the 2-D wavefields are SM-resident (shared memory + "
-                                   "registers), so the fraction may exceed 1: HBM is not the binding roof here, "
-                                   "FP32 issue is (see DESIGN.md)",
+                           "note": "achieved = ALGORITHMIC bytes per launch (20 B fwd / 32 B adj+img per grid-point-step "
+                                   "x points x steps x shots) / live CUDA-event duration. The 2-D wavefields are "
+                                   "SM-resident (shared memory + registers): real DRAM traffic (`traffic`, ncu) is "
+                                   "only the u.dt2 history, 17x below the algorithmic bytes, so HBM is not the binding "
+                                   "roof of this kernel - instruction issue / barrier latency is (DESIGN.md 4.2)",
                            "kernels": kern}
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(sample_shots=8)

@@ -259,17 +259,33 @@ def _is_l2(misfit_func):
     return misfit_func is least_square or getattr(misfit_func, '__name__', '') == 'least_square'
 
 
-def _stack_dev(receivers, shots, cache_owner, tag):
+def _stack_dev(receivers, shots, cache_owner, tag, stream=None):
     """[nshots, nt, nrec] device tensor of a list of Receivers; re-used while the SAME list object is
-    passed again (a new list - e.g. fresh host data every call - is uploaded again)."""
+    passed again and no record's host view has been handed out since (``.data`` access = possibly new
+    host data = upload again). With ``stream`` the uploads are issued on that (copy) stream from the
+    records' pinned host buffers, so they overlap the forward sweep."""
     import torch
     cache = cache_owner.__dict__.setdefault('_dev_stacks', {})
     hit = cache.get(tag)
-    if hit is not None and hit[0] is receivers and hit[1] == tuple(shots) and \
-            all(receivers[i]._sdata._newer is None and receivers[i]._sdata._dev is not None for i in shots):
+    versions = tuple(receivers[i]._sdata._hver for i in shots)
+    if hit is not None and hit[0] is receivers and hit[1] == tuple(shots) and hit[3] == versions:
         return hit[2]
-    t = torch.stack([receivers[i]._sdata.dev() for i in shots]).contiguous()
-    cache[tag] = (receivers, tuple(shots), t)
+    sd0 = receivers[shots[0]]._sdata
+    if hit is not None and tuple(hit[2].shape) == (len(shots),) + sd0.shape:
+        t = hit[2]
+    else:
+        t = torch.empty((len(shots),) + sd0.shape, dtype=torch.float32, device='cuda')
+    if stream is not None:
+        stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream()):
+        for k, i in enumerate(shots):
+            sd = receivers[i]._sdata
+            if sd._newer == 'dev' or sd._host is None:
+                t[k].copy_(sd.dev())                                   # record lives on the device
+            else:
+                t[k].copy_(sd._host_t if sd._host_t is not None else torch.from_numpy(sd._host),
+                           non_blocking=True)
+    cache[tag] = (receivers, tuple(shots), t, versions)
     return t
 
 
@@ -278,11 +294,17 @@ def _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_gr
     import torch
     lib = _lib.lib()
     shots = survey.shots
+    l2 = _is_l2(misfit_func)
+    if l2:
+        # observed / direct-wave records go up on a copy stream while the forward sweep runs
+        if getattr(survey, '_copy_stream', None) is None:
+            survey._copy_stream = torch.cuda.Stream()
+        obs_d = _stack_dev(obs, shots, survey, 'obs', survey._copy_stream)
+        dw_d = _stack_dev(direct_wave, shots, survey, 'dw', survey._copy_stream) if direct_wave is not None else None
     syn = survey.forward(save=calc_grad, illum=calc_grad)
-    if _is_l2(misfit_func):
+    if l2:
         # on-device least squares (misfit/misfit.py:5-9) incl. direct-wave subtraction (fwi.py:146-150)
-        obs_d = _stack_dev(obs, shots, survey, 'obs')
-        dw_d = _stack_dev(direct_wave, shots, survey, 'dw') if direct_wave is not None else None
+        torch.cuda.current_stream().wait_stream(survey._copy_stream)
         if getattr(survey, '_res', None) is None:
             survey._res = torch.empty_like(syn)
             survey._fval = torch.zeros(1, dtype=torch.float64, device='cuda')

@@ -68,6 +68,7 @@ class _SparseData(object):
         self._host_t = None
         self._dev = None
         self._newer = None
+        self._hver = 0          # bumped whenever the host view is handed out (it may then be modified)
 
     def host(self):
         from .grid import cuda_available
@@ -86,6 +87,7 @@ class _SparseData(object):
             else:
                 self._host[...] = self._dev.cpu().numpy()
         self._newer = 'host'
+        self._hver += 1
         return self._host
 
     def dev(self, write=False):
