@@ -90,23 +90,25 @@ static __device__ __forceinline__ float4 img4(float4 g, float4 d2, float4 v)    
                        __fmaf_rn(-d2.w, v.w, g.w));
 }
 
-template <int R, int NDIM, int IMG, int MINB>
-__global__ void __launch_bounds__(256, MINB) step_kernel(const __grid_constant__ StepArgs a)
+// TZQ x TR: tile shape in float4 columns x rows (threads = TZQ*TR); MINB: minimum resident CTAs per SM.
+template <int R, int NDIM, int IMG, int MINB, int TZQ = 16, int TR = 16>
+__global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_constant__ StepArgs a)
 {
-    constexpr int TR = 16;                 // rows per tile
+    constexpr int NT = TZQ * TR;           // threads per CTA
+    constexpr int TZ = 4 * TZQ;            // z cells per tile
     constexpr int RZ4 = (R + 3) / 4;       // z-halo width in float4
     constexpr int ZH = 4 * RZ4;            // z-halo width in floats
-    constexpr int SW = 64 + 2 * ZH;        // shared row width (floats)
+    constexpr int SW = TZ + 2 * ZH;        // shared row width (floats)
     constexpr int SROWS = TR + 2 * R;
-    constexpr int NHALO = 2 * R * 16 + TR * 2 * RZ4;
-    constexpr int NH = (NHALO + 255) / 256;
+    constexpr int NHALO = 2 * R * TZQ + TR * 2 * RZ4;
+    constexpr int NH = (NHALO + NT - 1) / NT;
     constexpr int NQ = (NDIM == 3) ? 2 * R + 1 : 1;
     constexpr int QC = (NDIM == 3) ? R : 0;
 
     __shared__ __align__(16) float tile[2][SROWS][SW];
 
-    const int tz = threadIdx.x, tr = threadIdx.y, tid = tr * 16 + tz;
-    const int ztile0 = blockIdx.x * 64;
+    const int tz = threadIdx.x, tr = threadIdx.y, tid = tr * TZQ + tz;
+    const int ztile0 = blockIdx.x * TZ;
     const int z0 = ztile0 + tz * 4;
     const int r0 = blockIdx.y * TR;
     const int r = r0 + tr;
@@ -122,19 +124,19 @@ __global__ void __launch_bounds__(256, MINB) step_kernel(const __grid_constant__
     int hsm[NH];           // shared offset (floats) inside one buffer, or -1
 #pragma unroll
     for (int i = 0; i < NH; i++) {
-        const int h = tid + i * 256;
+        const int h = tid + i * NT;
         int srow = -1, scol = 0, gz = 0;
-        if (h < 2 * R * 16) {
-            const int hr = h >> 4, hz = h & 15;
+        if (h < 2 * R * TZQ) {
+            const int hr = h / TZQ, hz = h % TZQ;
             srow = (hr < R) ? hr : hr + TR;
             scol = ZH + 4 * hz;
             gz = ztile0 + 4 * hz;
         } else if (h < NHALO) {
-            const int j = h - 2 * R * 16;
+            const int j = h - 2 * R * TZQ;
             const int row = j / (2 * RZ4), c = j % (2 * RZ4);
             srow = R + row;
             if (c < RZ4) { scol = 4 * c; gz = ztile0 - ZH + 4 * c; }
-            else { scol = ZH + 64 + 4 * (c - RZ4); gz = ztile0 + 64 + 4 * (c - RZ4); }
+            else { scol = ZH + TZ + 4 * (c - RZ4); gz = ztile0 + TZ + 4 * (c - RZ4); }
         }
         hsm[i] = (srow >= 0) ? srow * SW + scol : -1;
         const int gr = r0 - R + srow;
@@ -382,24 +384,39 @@ static int launch_async(const StepArgs &a, dim3 grid, cudaStream_t st)
     return 0;
 }
 
-static const int g_minb = []() { const char *e = getenv("B2FWI_MINB"); return e ? atoi(e) : 2; }();
 static const int g_async = []() { const char *e = getenv("B2FWI_ASYNC_KERNEL"); return e ? atoi(e) : -1; }();   // -1: auto
+
+// measured on 592^3 so=8 forward (fraction of HBM copy bandwidth): 0: 0.714, 1: 0.740, 2: 0.714, 3: 0.744
+static const int g_tile = []() { const char *e = getenv("B2FWI_TILE"); return e ? atoi(e) : 3; }();
+static void tile_shape(int ndim, int *tz, int *tr, int *blocks_per_sm)
+{
+    // 3-D tile variants (A/B via B2FWI_TILE): 0: 64z x 16 rows, 1: 128z x 8, 2: 64z x 32, 3: 128z x 16
+    *tz = 64; *tr = 16; *blocks_per_sm = 2;
+    if (ndim != 3) return;
+    if (g_tile == 1) { *tz = 128; *tr = 8; }
+    else if (g_tile == 2) { *tz = 64; *tr = 32; *blocks_per_sm = 1; }
+    else if (g_tile == 3) { *tz = 128; *tr = 16; *blocks_per_sm = 1; }
+}
 
 template <int R, int NDIM>
 static int launch_step_img(const Layout &L, const StepArgs &a, int img, dim3 grid, cudaStream_t st)
 {
+    if (NDIM == 3 && g_tile != 0 && img != 1 && R <= 4) {
+#define B2_TILE(IMGV)                                                                                           \
+        if (g_tile == 1) step_kernel<R, NDIM, IMGV, 2, 32, 8><<<grid, dim3(32, 8, 1), 0, st>>>(a);              \
+        else if (g_tile == 2) step_kernel<R, NDIM, IMGV, 1, 16, 32><<<grid, dim3(16, 32, 1), 0, st>>>(a);       \
+        else step_kernel<R, NDIM, IMGV, 1, 32, 16><<<grid, dim3(32, 16, 1), 0, st>>>(a);
+        if (img == 0) { B2_TILE(0) } else { B2_TILE(2) }
+#undef B2_TILE
+        B2_CUDA(cudaGetLastError());
+        count_launch();
+        return 0;
+    }
     dim3 block(16, 16, 1);
-    const bool three = (NDIM == 3) && g_minb == 3 && R <= 4;
     switch (img) {
-    case 0:
-        if (three) step_kernel<R, NDIM, 0, (R <= 4 ? 3 : 2)><<<grid, block, 0, st>>>(a);
-        else step_kernel<R, NDIM, 0, 2><<<grid, block, 0, st>>>(a);
-        break;
+    case 0: step_kernel<R, NDIM, 0, 2><<<grid, block, 0, st>>>(a); break;
     case 1: step_kernel<R, NDIM, 1, 2><<<grid, block, 0, st>>>(a); break;
-    case 2:
-        if (three) step_kernel<R, NDIM, 2, (R <= 4 ? 3 : 2)><<<grid, block, 0, st>>>(a);
-        else step_kernel<R, NDIM, 2, 2><<<grid, block, 0, st>>>(a);
-        break;
+    case 2: step_kernel<R, NDIM, 2, 2><<<grid, block, 0, st>>>(a); break;
     default: set_error("bad imaging mode %d", img); return B2FWI_EINVAL;
     }
     B2_CUDA(cudaGetLastError());
@@ -412,14 +429,16 @@ int pick_chunk(const Layout &L)
     // 3-D: split the streamed axis so that the grid is a whole number of waves of resident CTAs
     // (148 SMs x 2 CTAs); each chunk re-reads 2R planes of pipeline priming.
     if (L.ndim != 3) return 1;
+    int tzc, trc, bps;
+    tile_shape(L.ndim, &tzc, &trc, &bps);
     static int n_slots = 0;
     if (n_slots == 0) {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess)
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        n_slots = g_minb * sms;
+        n_slots = bps * sms;
     }
-    const long tiles = (long)((L.nz + 63) / 64) * ((L.nr + 15) / 16);
+    const long tiles = (long)((L.nz + tzc - 1) / tzc) * ((L.nr + trc - 1) / trc);
     int best_nc = 1;
     double best_cost = 1e30;
     const int max_nc = L.np / (4 * L.R) > 0 ? L.np / (4 * L.R) : 1;
@@ -444,7 +463,10 @@ int launch_step(const Layout &L, StepArgs a, int img, cudaStream_t st)
     a.np = L.np; a.nr = L.nr; a.nz = L.nz; a.halo = L.halo; a.sp = L.sp; a.sr = L.sr;
     if (a.chunk <= 0) a.chunk = pick_chunk(L);
     const int nchunks = (L.ndim == 3) ? (L.np + a.chunk - 1) / a.chunk : 1;
-    dim3 grid((L.nz + 63) / 64, (L.nr + 15) / 16, nchunks);
+    int tzc, trc, bps;
+    tile_shape(L.ndim, &tzc, &trc, &bps);
+    if (L.R > 4 || img == 1) { tzc = 64; trc = 16; }      // variants exist for so <= 8, imaging from u.dt2 / forward
+    dim3 grid((L.nz + tzc - 1) / tzc, (L.nr + trc - 1) / trc, nchunks);
 #define B2_CASE(r)                                                              \
     case r:                                                                     \
         if (L.ndim == 3 && img == 0 && use_async(r)) return launch_async<r, 0>(a, grid, st);   \
