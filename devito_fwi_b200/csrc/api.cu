@@ -155,6 +155,7 @@ int b2fwi_forward(const b2fwi_grid *g, const float *vp, const float *coef, float
     memset(&a, 0, sizeof(a));
     fill_stencil_weights(L, &a);
     a.c1 = coef; a.c2 = coef + L.elems;
+    a.box = reinterpret_cast<const int *>(coef + 2 * L.elems);
     a.inv_dt2 = 1.f / (dt * dt);
     a.chunk = pick_chunk(L);
     for (int time = time_m; time <= time_M; time++) {
@@ -203,6 +204,7 @@ static int backward(const b2fwi_grid *g, const float *vp, const float *coef, flo
     memset(&a, 0, sizeof(a));
     fill_stencil_weights(L, &a);
     a.c1 = coef; a.c2 = coef + L.elems;
+    a.box = reinterpret_cast<const int *>(coef + 2 * L.elems);
     a.inv_dt2 = 1.f / (dt * dt);
     a.chunk = pick_chunk(L);
     a.grad = grad;

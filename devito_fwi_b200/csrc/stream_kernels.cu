@@ -144,6 +144,12 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
         hoff[i] = ok ? (NDIM == 3 ? H * a.sp : 0) + (int64_t)(gr + H) * a.sr + (gz + H) : -1;
     }
 
+    // undamped interior (coef[0] == 1 exactly): this thread never reads c1 for planes inside the box
+    const int blo_p = __ldg(a.box + 0), bhi_p = __ldg(a.box + 1);
+    const bool in_box = __ldg(a.box + 6) == 1 && r >= __ldg(a.box + 2) && r < __ldg(a.box + 3) &&
+                        z0 >= __ldg(a.box + 4) && z0 + 3 < __ldg(a.box + 5);
+    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+
     // ---- prologue: register pipeline along the plane axis, halo of the first plane
     float4 q[NQ];
     if (NDIM == 3) {
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
                 float4 g4 = zero4(), h0 = zero4(), h1 = zero4(), h2 = zero4(), il = zero4();
                 if (active) {
                     prev = ld4(a.prev + own0 + pofs);
-                    c1 = ldg4(a.c1 + own0 + pofs);
+                    c1 = (in_box && p >= blo_p && p < bhi_p) ? one4 : ldg4(a.c1 + own0 + pofs);
                     c2 = ldg4(a.c2 + own0 + pofs);
                     if (IMG != 0) {
                         g4 = ld4(a.grad + own0 + pofs);
@@ -556,12 +562,55 @@ __global__ void coeff_kernel(const float *__restrict__ vp, const float *__restri
     c2[i] = b;
 }
 
+// Index box of the undamped interior. The sponge profile is a sum of non-negative 1-D profiles
+// (seismic/model.py:31-49), so {c1 == 1} is a box; its extent per dimension is read off the three lines
+// through the grid centre, then verified over the whole grid (box_verify_kernel) - an arbitrary damping
+// field simply ends up with valid = 0 and every point reads c1.
+__global__ void box_lines_kernel(const float *__restrict__ c1, int np, int nr, int nz, int64_t sp, int64_t sr,
+                                 int64_t base, int *__restrict__ box)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n[3] = {np, nr, nz};
+    const int64_t st[3] = {sp, sr, 1};
+    const int c[3] = {np / 2, nr / 2, nz / 2};
+    const int64_t centre = base + c[0] * sp + c[1] * sr + c[2];
+    const bool ok = c1[centre] == 1.0f;
+    for (int d = 0; d < 3; d++) {
+        int lo = c[d], hi = c[d] + 1;
+        if (ok) {
+            while (lo > 0 && c1[centre + (int64_t)(lo - 1 - c[d]) * st[d]] == 1.0f) lo--;
+            while (hi < n[d] && c1[centre + (int64_t)(hi - c[d]) * st[d]] == 1.0f) hi++;
+        }
+        box[2 * d] = lo;
+        box[2 * d + 1] = ok ? hi : lo;
+    }
+    box[6] = ok ? 1 : 0;
+    box[7] = 0;
+}
+
+__global__ void box_verify_kernel(const float *__restrict__ c1, int np, int nr, int nz, int64_t sp, int64_t sr,
+                                  int64_t base, int *__restrict__ box)
+{
+    const int lo_p = box[0], lo_r = box[2], lo_z = box[4];
+    const int64_t ep = box[1] - lo_p, er = box[3] - lo_r, ez = box[5] - lo_z;
+    const int64_t total = ep * er * ez;
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int z = lo_z + (int)(i % ez), r = lo_r + (int)((i / ez) % er), p = lo_p + (int)(i / (ez * er));
+        if (c1[base + p * sp + r * sr + z] != 1.0f) bad = true;
+    }
+    if (bad) atomicExch(box + 6, 0);
+}
+
 int launch_coeffs(const Layout &L, const float *vp, const float *damp, float dt, float *coef, cudaStream_t st)
 {
     const int64_t n = L.elems;
     coeff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(vp, damp, (double)dt, coef, coef + n, n);
+    int *box = reinterpret_cast<int *>(coef + 2 * n);
+    box_lines_kernel<<<1, 32, 0, st>>>(coef, L.np, L.nr, L.nz, L.sp, L.sr, L.base, box);
+    box_verify_kernel<<<1184, 256, 0, st>>>(coef, L.np, L.nr, L.nz, L.sp, L.sr, L.base, box);
     B2_CUDA(cudaGetLastError());
-    count_launch();
+    count_launch(3);
     return 0;
 }
 

@@ -11,6 +11,7 @@ struct StepArgs {
     const float *cur;      // u[t] / v[t]
     const float *prev;     // u[t-1] / v[t+1]
     const float *c1, *c2;  // update coefficients (b2fwi_prepare_coeffs)
+    const int *box;        // {lo_p, hi_p, lo_r, hi_r, lo_z, hi_z, valid}: inside, c1 == 1 exactly and is not read
     // imaging condition (IMG != 0): grad += -u.dt2 * cur
     float *grad;
     const float *h0, *h1, *h2;  // IMG==1: u[t-1], u[t], u[t+1];  IMG==2: h1 = u.dt2[t]

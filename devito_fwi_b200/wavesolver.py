@@ -141,7 +141,8 @@ class AcousticWaveSolver(object):
     def _coeffs(self, vp_dev, dt):
         import torch
         lib = _lib.lib()
-        coef = torch.empty((2,) + self.model.grid.slice_shape, dtype=torch.float32, device='cuda')
+        # two coefficient slices + B2FWI_COEF_TAIL floats (interior box written by the library)
+        coef = torch.empty(2 * self.model.grid.slice_elems + 8, dtype=torch.float32, device='cuda')
         g = self._gs()
         _lib.check(lib.b2fwi_prepare_coeffs(ctypes.byref(g), _ptr(vp_dev), _ptr(self._damp_dev()),
                                             ctypes.c_float(dt), _ptr(coef), _stream()))
