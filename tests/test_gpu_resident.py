@@ -173,3 +173,44 @@ def test_fm_multi_and_host_misfit_plugin_roundtrip():
     f2, g2, _ = fwi.fwi_obj_multi(g_init, obs, fwi.least_square, None, None, False, True)
     assert np.isclose(f, f2, rtol=1e-6) and rel_l2(g, g2) < 1e-6
     assert isinstance(res[0], np.ndarray) and res[0].shape == (g_init.nt, 201)
+
+
+def test_gradient_taylor_and_linearity():
+    """Property tests through the product path (patterns of seismic/self_adjoint/test_wavesolver_iso.py):
+    linearity F(a s) = a F(s), and the Taylor test of the objective/gradient pair
+    f(m + h dm) - f(m) - h <g, dm> = O(h^2) with the un-preconditioned, un-masked gradient (fwi.py:236-246)."""
+    import devito_fwi_b200 as b
+    from devito_fwi_b200 import configs, fwi
+    g_true, g_init = configs.circle(space_order=4, nsrc=2)
+    obs = fwi.fm_multi(g_true)
+    # linearity in the source amplitude (resident engine, batched shots)
+    from devito_fwi_b200.resident import ResidentSurvey
+    sv = ResidentSurvey(g_init, [0, 1])
+    d1 = sv.forward().clone()
+    # Scaling by a power of two is exact in IEEE arithmetic EXCEPT in the denormal range, which the numerical
+    # precursor ahead of the wavefront crosses (1e-44 .. 1e-38); one differing bit there decorrelates all later
+    # roundings, so the two runs are two fp32 realisations that differ by the round-off noise floor (~1e-6).
+    sv.src.mul_(2.0)
+    d2 = sv.forward().clone()
+    assert rel_l2(d2.cpu().numpy(), 2.0 * d1.cpu().numpy()) < 1e-5
+    sv.src.mul_(1.5)
+    d3 = sv.forward().clone()
+    assert rel_l2(d3.cpu().numpy(), 3.0 * d1.cpu().numpy()) < 1e-5
+
+    shape = g_init.model.shape
+    m0 = (1. / (g_init.model.vp.data[40:-40, 40:-40].astype(np.float64) ** 2)).ravel()
+    f0, g0, _ = fwi.fwi_loss(m0, g_init, obs, fwi.least_square, None, None, False, True)
+    rng = np.random.default_rng(3)
+    xx, zz = np.meshgrid(np.arange(shape[0]), np.arange(shape[1]), indexing='ij')
+    dm = (1e-3 * np.exp(-((xx - 100) ** 2 + (zz - 90) ** 2) / 800.)).ravel()     # smooth slowness bump
+    errs = []
+    hs = [1.0, 0.5, 0.25]
+    for h in hs:
+        fh, _, _ = fwi.fwi_loss(m0 + h * dm, g_init, obs, fwi.least_square, None, None, False, False)
+        errs.append((abs(fh - f0), abs(fh - f0 - h * np.dot(g0, dm))))
+    print("Taylor test: |f(m+h dm)-f(m)|, |... - h<g,dm>|:", errs)
+    # first-order remainder halves, second-order remainder quarters (within fp32 noise)
+    for k in range(len(hs) - 1):
+        assert 1.7 < errs[k][0] / errs[k + 1][0] < 2.3
+        assert errs[k][1] / errs[k + 1][1] > 3.3
+    assert errs[-1][1] < 0.05 * errs[-1][0]
