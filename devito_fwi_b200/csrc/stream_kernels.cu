@@ -36,7 +36,7 @@ static __device__ __forceinline__ float d2u_of(float um, float uc, float up, flo
 //   The pipeline is addressed circularly: plane offset i in -R..R lives in q[(j + R + i) % NQ] (j: rotation).
 template <int R, int NDIM, int SW>
 static __device__ __forceinline__ float4 point_update(const StepArgs &a, const float4 *q, int j, const float *ctr,
-                                                     float4 prev, float4 c1, float4 c2, int z0)
+                                                     float4 prev, float4 c1, float4 c2, int zvalid)
 {
     constexpr int RZ4 = (R + 3) / 4, ZH = 4 * RZ4;
     constexpr int NQ = (NDIM == 3) ? 2 * R + 1 : 1;
@@ -73,21 +73,22 @@ static __device__ __forceinline__ float4 point_update(const StepArgs &a, const f
     // u+ = u + c1 (u - u-) + c2 L(u)
     const float4 t = fma4(c1, add4(C, make_float4(-prev.x, -prev.y, -prev.z, -prev.w)), C);
     float4 o = fma4(c2, lap, t);
-    if (z0 + 1 >= a.nz) o.y = 0.f;
-    if (z0 + 2 >= a.nz) o.z = 0.f;
-    if (z0 + 3 >= a.nz) o.w = 0.f;
+    if (zvalid < 4) {                     // only the last, partial quad of a row: keep the pitch padding zero
+        if (zvalid < 2) o.y = 0.f;
+        if (zvalid < 3) o.z = 0.f;
+        o.w = 0.f;
+    }
     return o;
 }
 
+// packed forms of d2u_of / the imaging update (FFMA2 etc. round exactly like their scalar counterparts)
 static __device__ __forceinline__ float4 d2u4(float4 um, float4 uc, float4 up, float inv_dt2)
 {
-    return make_float4(d2u_of(um.x, uc.x, up.x, inv_dt2), d2u_of(um.y, uc.y, up.y, inv_dt2),
-                       d2u_of(um.z, uc.z, up.z, inv_dt2), d2u_of(um.w, uc.w, up.w, inv_dt2));
+    return mul4s(inv_dt2, add4(fma4s(-2.f, uc, um), up));
 }
 static __device__ __forceinline__ float4 img4(float4 g, float4 d2, float4 v)     // grad += -u.dt2 * v
 {
-    return make_float4(__fmaf_rn(-d2.x, v.x, g.x), __fmaf_rn(-d2.y, v.y, g.y), __fmaf_rn(-d2.z, v.z, g.z),
-                       __fmaf_rn(-d2.w, v.w, g.w));
+    return fma4(make_float4(-d2.x, -d2.y, -d2.z, -d2.w), v, g);
 }
 
 // TZQ x TR: tile shape in float4 columns x rows (threads = TZQ*TR); MINB: minimum resident CTAs per SM.
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
     const int r0 = blockIdx.y * TR;
     const int r = r0 + tr;
     const bool active = (r < a.nr) && (z0 < a.nz);
+    const int zvalid = min(4, a.nz - z0);      // valid lanes of this thread's float4
     const int p_begin = (NDIM == 3) ? (int)blockIdx.z * a.chunk : 0;
     const int p_end = (NDIM == 3) ? min(p_begin + a.chunk, a.np) : 1;
     const int64_t H = a.halo;
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
     // plane loop; for R <= 4 it is unrolled NQ times so that the register pipeline rotates through
     // compile-time slots instead of being shifted (2R float4 moves per plane otherwise)
     constexpr int UNR = (NDIM == 3 && R <= 4) ? NQ : 1;
+    int64_t pofs_run = (NDIM == 3) ? (int64_t)p_begin * a.sp : 0;      // plane offset, advanced by one plane per iteration
     for (int pb = p_begin; pb < p_end; pb += UNR) {
 #pragma unroll
         for (int j = 0; j < UNR; j++) {
@@ -176,7 +179,8 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
             if (p < p_end) {
                 const int buf = (p - p_begin) & 1;
                 float *tb = &tile[buf][0][0];
-                const int64_t pofs = (NDIM == 3) ? (int64_t)p * a.sp : 0;
+                const int64_t pofs = pofs_run;
+                pofs_run += a.sp;
                 // stage plane p
                 st4(tb + (R + tr) * SW + ZH + 4 * tz, q[(j + QC) % NQ]);
 #pragma unroll
@@ -184,8 +188,7 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
                     if (hsm[i] >= 0) st4(tb + hsm[i], hreg[i]);
 
                 // pointwise operands of plane p
-                float4 prev = zero4(), c1 = zero4(), c2 = zero4();
-                float4 g4 = zero4(), h0 = zero4(), h1 = zero4(), h2 = zero4(), il = zero4();
+                float4 prev, c1, c2, g4, h0, h1, h2, il;      // only defined (and only used) by active threads
                 if (active) {
                     prev = ld4(a.prev + own0 + pofs);
                     c1 = (in_box && p >= blo_p && p < bhi_p) ? one4 : ldg4(a.c1 + own0 + pofs);
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
                 if (p + 1 < p_end) {
                     if (NDIM == 3) {
                         const int pn = p + R + 1;
-                        if (active && pn < a.np) qn = ld4(a.cur + own0 + (int64_t)pn * a.sp);
+                        if (active && pn < a.np) qn = ld4(a.cur + own0 + pofs + (int64_t)(R + 1) * a.sp);
                     }
 #pragma unroll
                     for (int i = 0; i < NH; i++)
@@ -215,15 +218,17 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
 
                 if (active) {
                     const float4 C = q[(j + QC) % NQ];
-                    const float4 o = point_update<R, NDIM, SW>(a, q, j, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, z0);
+                    const float4 o = point_update<R, NDIM, SW>(a, q, j, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, zvalid);
                     st4(a.out + own0 + pofs, o);
                     if (IMG != 0) st4(a.grad + own0 + pofs, img4(g4, IMG == 1 ? d2u4(h0, h1, h2, a.inv_dt2) : h1, C));
                     if (a.illum) st4(a.illum + own0 + pofs, fma4(C, C, il));
                     if (a.d2u) {
                         float4 d = d2u4(prev, C, o, a.inv_dt2);
-                        if (z0 + 1 >= a.nz) d.y = 0.f;
-                        if (z0 + 2 >= a.nz) d.z = 0.f;
-                        if (z0 + 3 >= a.nz) d.w = 0.f;
+                        if (zvalid < 4) {
+                            if (zvalid < 2) d.y = 0.f;
+                            if (zvalid < 3) d.z = 0.f;
+                            d.w = 0.f;
+                        }
                         st4(a.d2u + own0 + pofs, d);
                     }
                 }
@@ -274,6 +279,7 @@ __global__ void __launch_bounds__(256, 2) step3d_async_kernel(const __grid_const
     const int r0 = blockIdx.y * TR;
     const int r = r0 + tr;
     const bool active = (r < a.nr) && (z0 < a.nz);
+    const int zvalid = min(4, a.nz - z0);      // valid lanes of this thread's float4
     const int p_begin = (int)blockIdx.z * a.chunk;
     const int p_end = min(p_begin + a.chunk, a.np);
     const int64_t H = a.halo;
@@ -354,15 +360,15 @@ __global__ void __launch_bounds__(256, 2) step3d_async_kernel(const __grid_const
             const float4 *ax = aux + (slot * NAUX) * 256 + tid;
             const float4 prev = ax[0], c1 = ax[256], c2 = ax[512];
             const float4 C = q[QC];
-            const float4 o = point_update<R, 3, SW>(a, q, 0, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, z0);
+            const float4 o = point_update<R, 3, SW>(a, q, 0, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, zvalid);
             st4(a.out + own0 + pofs, o);
             if (IMG == 2) st4(a.grad + own0 + pofs, img4(ax[768], ax[1024], C));
             if (a.illum) st4(a.illum + own0 + pofs, fma4(C, C, il));
             if (a.d2u) {
                 float4 d = d2u4(prev, C, o, a.inv_dt2);
-                if (z0 + 1 >= a.nz) d.y = 0.f;
-                if (z0 + 2 >= a.nz) d.z = 0.f;
-                if (z0 + 3 >= a.nz) d.w = 0.f;
+                if (zvalid < 2) d.y = 0.f;
+                if (zvalid < 3) d.z = 0.f;
+                if (zvalid < 4) d.w = 0.f;
                 st4(a.d2u + own0 + pofs, d);
             }
         }
