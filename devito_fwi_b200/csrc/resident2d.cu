@@ -126,6 +126,9 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
         }
     }
     const float4 szq = tactive ? __ldg(reinterpret_cast<const float4 *>(a.sz + 4 * qi)) : z4();
+    bool push_any = false;
+#pragma unroll
+    for (int r = 0; r < P; r++) push_any = push_any || (((flags >> (4 * r)) & 12ull) != 0ull);
     const unsigned long long imask = tactive ? a.thr_mask[(int64_t)sc * T + tid] : 0ull;
     const int ibase = tactive ? a.thr_base[(int64_t)sc * T + tid] : 0;
 
@@ -268,8 +271,6 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                     }
                     const float4 un = add4(Cq, dn);
                     sts4(rn, un);
-                    if (f & 4u) sts4_cluster(prv_n + (rn - nxt_s) + prev_delta, un);
-                    if (f & 8u) sts4_cluster(nex_n + (rn - nxt_s) - next_delta, un);
                     if (MODE == 0 && (f & 2u)) {
                         {
                             if (has_hist) {
@@ -289,6 +290,21 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                 bp += Bstride;
                 opaque(rw); opaque(ro); opaque(rn); opaque(ra);
                 opaque_ptr(hp); opaque_ptr(bp);
+            }
+        }
+        // push this CTA's R boundary rows into the neighbours' halo rows (distributed shared memory). Done after the
+        // row loop, by the few threads that own boundary rows, re-reading what they just wrote: keeps the ~10
+        // address-conversion instructions of a remote store out of every row of every thread.
+        if (push_any) {
+#pragma unroll
+            for (int r = 0; r < P; r++) {
+                const unsigned f = (unsigned)(flags >> (4 * r)) & 0xFu;
+                if (f & 12u) {
+                    const uint32_t off = own_off + (uint32_t)r * pitchB;
+                    const float4 un = lds4(nxt_s + off);
+                    if (f & 4u) sts4_cluster(prv_n + off + prev_delta, un);
+                    if (f & 8u) sts4_cluster(nex_n + off - next_delta, un);
+                }
             }
         }
         if (more) {
