@@ -214,3 +214,17 @@ def test_gradient_taylor_and_linearity():
         assert 1.7 < errs[k][0] / errs[k + 1][0] < 2.3
         assert errs[k][1] / errs[k + 1][1] > 3.3
     assert errs[-1][1] < 0.05 * errs[-1][0]
+
+
+def test_marmousi_fwi_example_reduces_the_objective():
+    """A few L-BFGS iterations of the Marmousi L2 FWI driver (examples/marmousi_fwi.py) on 5 shots."""
+    import sys
+    import examples.marmousi_fwi as ex
+    argv = sys.argv
+    sys.argv = ["marmousi_fwi.py", "--nsrc", "5", "--maxiter", "3", "--odir", "/tmp/b2fwi_result"]
+    try:
+        history = ex.main()
+    finally:
+        sys.argv = argv
+    assert len(history) >= 3
+    assert min(history) < 0.8 * history[0]
