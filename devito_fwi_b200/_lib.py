@@ -93,6 +93,8 @@ PROTOTYPES = {
     "b2fwi_res2d_gradient": (ctypes.c_int, [_G, _P, _P, _P, _P, _F, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P]),
     "b2fwi_window_mask_accumulate": (ctypes.c_int, [_I, _I, _P, ctypes.c_int64, _I, _P, _P, _P]),
     "b2fwi_window_mask_accumulate_batch": (ctypes.c_int, [_I, _I, _I, _P, ctypes.c_int64, ctypes.c_int64, _I, _P, _P, _P]),
+    "b2fwi_w1d_misfit": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, ctypes.c_double, _P, _P, _P, _P]),
+    "b2fwi_w1d_scratch_bytes": (ctypes.c_int64, [_I, _I, _I]),
     "b2fwi_l2_misfit": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, _P, _P, _P]),
 }
 

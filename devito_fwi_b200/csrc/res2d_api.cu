@@ -82,6 +82,143 @@ __global__ void l2_stage2(const double *__restrict__ partial, int nblocks, doubl
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 1-D quadratic-Wasserstein misfit, trace by trace (misfit/misfit.py:20-67, qWasserstein(method='1d',
+// trans_type='linear')): signals are shifted positive by c = gamma * max(0, -min) (one c per shot record),
+// normalised to unit mass, T = G^-1(F) by linear interpolation of the cumulative distributions,
+//   loss = 0.5 sum (t - T)^2 mu,   grad = (cumsum(t - T) - sum(t - T) - <.., mu>) / mass.
+// Follows the reference's numeric types: fp32 signals and fp32 running sums (np.cumsum), fp64 from np.interp on.
+__global__ void w1d_min_kernel(const float *__restrict__ syn, const float *__restrict__ obs, const float *__restrict__ dw,
+                               int64_t n_per_shot, float *__restrict__ cmin)
+{
+    __shared__ float sh[256];
+    const int shot = blockIdx.x;
+    const int64_t base = (int64_t)shot * n_per_shot;
+    float m = 3.4e38f;
+    for (int64_t i = threadIdx.x; i < n_per_shot; i += blockDim.x) {
+        const float d = dw ? dw[base + i] : 0.f;
+        m = fminf(m, fminf(syn[base + i] - d, obs[base + i] - d));
+    }
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = fminf(sh[threadIdx.x], sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) cmin[shot] = sh[0];
+}
+
+// numpy's float32 `sum()` (pairwise summation, 8 accumulators per <=128-element block, numpy/core/src/umath/
+// loops_utils.h) reproduced exactly: the trace mass enters the normalisation, and a 1-ulp difference in it
+// shows up as 3e-5 in the adjoint source through the inverse-CDF interpolation.
+struct ShiftedTrace {
+    const float *a, *dw;
+    int64_t stride;
+    float c;
+    __device__ float operator[](int k) const
+    {
+        const float d = dw ? dw[(int64_t)k * stride] : 0.f;
+        return __fadd_rn(__fsub_rn(a[(int64_t)k * stride], d), c);
+    }
+};
+
+static __device__ float pairwise_sum_f32(const ShiftedTrace &v, int i0, int n)
+{
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; i++) res = __fadd_rn(res, v[i0 + i]);
+        return res;
+    }
+    if (n <= 128) {
+        float r[8];
+        for (int j = 0; j < 8; j++) r[j] = v[i0 + j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; j++) r[j] = __fadd_rn(r[j], v[i0 + i + j]);
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; i++) res = __fadd_rn(res, v[i0 + i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(pairwise_sum_f32(v, i0, n2), pairwise_sum_f32(v, i0 + n2, n - n2));
+}
+
+__global__ void w1d_trace_kernel(const float *__restrict__ syn, const float *__restrict__ obs, const float *__restrict__ dw,
+                                 int nt, int nrec, int nshots, double gamma, const float *__restrict__ cmin,
+                                 float *__restrict__ G, double *__restrict__ D, float *__restrict__ grad_out,
+                                 double *__restrict__ loss)
+{
+    const int tr = blockIdx.x * blockDim.x + threadIdx.x;       // global trace index: shot * nrec + receiver
+    if (tr >= nshots * nrec) return;
+    const int shot = tr / nrec, ir = tr - shot * nrec;
+    const int64_t base = (int64_t)shot * nt * nrec + ir;        // element (k, ir) at base + k*nrec
+    const float mn = cmin[shot];
+    // c = (-min) * gamma evaluated in fp32, as numpy does for an fp32 scalar times a python float (NEP 50)
+    const float c = (mn < 0.f) ? __fmul_rn(-mn, (float)gamma) : 0.f;
+    float *g = G + (int64_t)tr;                                  // scratch, element k at g[k * ntraces]
+    double *dd = D + (int64_t)tr;
+    const int64_t ntr = (int64_t)nshots * nrec;
+    const ShiftedTrace vf{syn + base, dw ? dw + base : nullptr, nrec, c}, vg{obs + base, dw ? dw + base : nullptr, nrec, c};
+    const float mass_f = pairwise_sum_f32(vf, 0, nt), mass_g = pairwise_sum_f32(vg, 0, nt);
+    // G = cumsum(nu) in fp32
+    float acc = 0.f;
+    for (int k = 0; k < nt; k++) {
+        const float d = dw ? dw[base + (int64_t)k * nrec] : 0.f;
+        acc += ((obs[base + (int64_t)k * nrec] - d) + c) / mass_g;
+        g[(int64_t)k * ntr] = acc;
+    }
+    // sweep F = cumsum(mu); T = interp(F, G, t); both sequences are non-decreasing -> one forward pointer
+    const double h = 1.0 / (double)(nt - 1);
+    float F = 0.f;
+    int j = 0;                                                   // largest j with G[j] <= F (searchsorted side='right' - 1)
+    const float G0 = g[0], Glast = g[(int64_t)(nt - 1) * ntr];
+    double lsum = 0.0, dsum = 0.0;
+    for (int k = 0; k < nt; k++) {
+        const float d = dw ? dw[base + (int64_t)k * nrec] : 0.f;
+        const float mu = ((syn[base + (int64_t)k * nrec] - d) + c) / mass_f;
+        F += mu;
+        double T;
+        if (F <= G0) T = 0.0;                 // np.interp: left value below the first knot
+        else if (F >= Glast) T = 1.0;         // right value (t[-1]) at / above the last knot
+        else {
+            while (j + 1 < nt - 1 && g[(int64_t)(j + 1) * ntr] <= F) j++;
+            const double x0 = (double)g[(int64_t)j * ntr], x1 = (double)g[(int64_t)(j + 1) * ntr];
+            const double t0 = j * h;
+            T = (x1 > x0) ? ((double)F - x0) * (h / (x1 - x0)) + t0 : t0;
+        }
+        const double dk = k * h - T;
+        dd[(int64_t)k * ntr] = dk;
+        lsum += dk * dk * (double)mu;
+        dsum += dk;
+    }
+    loss[tr] = 0.5 * lsum;
+    // grad = cumsum(d) - sum(d);  grad = (grad - sum(grad * mu)) / mass
+    double run = 0.0, gm = 0.0;
+    for (int k = 0; k < nt; k++) {
+        const float d = dw ? dw[base + (int64_t)k * nrec] : 0.f;
+        const float mu = ((syn[base + (int64_t)k * nrec] - d) + c) / mass_f;
+        run += dd[(int64_t)k * ntr];
+        gm += (run - dsum) * (double)mu;
+    }
+    run = 0.0;
+    for (int k = 0; k < nt; k++) {
+        run += dd[(int64_t)k * ntr];
+        grad_out[base + (int64_t)k * nrec] = (float)(((run - dsum) - gm) / (double)mass_f);
+    }
+}
+
+__global__ void sum_doubles_kernel(const double *__restrict__ v, int n, double *__restrict__ out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; i++) s += v[i];
+        out[0] += s;
+    }
+}
+
 static int fill_args(const b2fwi_grid *g, const b2fwi_res2d_plan *p, Res2dArgs *a)
 {
     Layout L;
@@ -274,6 +411,32 @@ int b2fwi_l2_misfit(const float *syn, const float *obs, const float *dw, int64_t
     B2_CUDA(cudaGetLastError());
     count_launch(2);
     return 0;
+}
+
+int b2fwi_w1d_misfit(const float *syn, const float *obs, const float *dw, int32_t nt, int32_t nrec, int32_t nshots,
+                     double gamma, float *adjsrc_out, double *fval_out, void *scratch, void *stream)
+{
+    B2_CHECK_ARG(syn && obs && adjsrc_out && fval_out && scratch && nt >= 2 && nrec >= 1 && nshots >= 1, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ntr = (int64_t)nshots * nrec;
+    // scratch layout: D[nt*ntr] doubles | loss[ntr] doubles | G[nt*ntr] floats | cmin[nshots] floats
+    double *D = reinterpret_cast<double *>(scratch);
+    double *loss = D + (int64_t)nt * ntr;
+    float *G = reinterpret_cast<float *>(loss + ntr);
+    float *cmin = G + (int64_t)nt * ntr;
+    w1d_min_kernel<<<nshots, 256, 0, st>>>(syn, obs, dw, (int64_t)nt * nrec, cmin);
+    w1d_trace_kernel<<<(unsigned)((ntr + 63) / 64), 64, 0, st>>>(syn, obs, dw, nt, nrec, nshots, gamma, cmin, G, D,
+                                                                 adjsrc_out, loss);
+    sum_doubles_kernel<<<1, 32, 0, st>>>(loss, (int)ntr, fval_out);
+    B2_CUDA(cudaGetLastError());
+    count_launch(3);
+    return 0;
+}
+
+int64_t b2fwi_w1d_scratch_bytes(int32_t nt, int32_t nrec, int32_t nshots)
+{
+    const int64_t ntr = (int64_t)nshots * nrec;
+    return ((int64_t)nt * ntr + ntr) * 8 + ((int64_t)nt * ntr + nshots) * 4 + 64;
 }
 
 }  // extern "C"

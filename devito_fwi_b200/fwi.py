@@ -259,6 +259,12 @@ def _is_l2(misfit_func):
     return misfit_func is least_square or getattr(misfit_func, '__name__', '') == 'least_square'
 
 
+def _is_w1d(misfit_func):
+    """The reference's qWasserstein(trans_type='linear', method='1d') instance (misfit/misfit.py:11-104)."""
+    return (type(misfit_func).__name__ == 'qWasserstein' and getattr(misfit_func, 'method', None) == '1d'
+            and getattr(misfit_func, 'trans_type', None) == 'linear')
+
+
 def _stack_dev(receivers, shots, cache_owner, tag, stream=None):
     """[nshots, nt, nrec] device tensor of a list of Receivers; re-used while the SAME list object is
     passed again and no record's host view has been handed out since (``.data`` access = possibly new
@@ -294,7 +300,8 @@ def _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_gr
     import torch
     lib = _lib.lib()
     shots = survey.shots
-    l2 = _is_l2(misfit_func)
+    w1d = _is_w1d(misfit_func)
+    l2 = _is_l2(misfit_func) or w1d          # misfits evaluated on the device
     if l2:
         # observed / direct-wave records go up on a copy stream while the forward sweep runs
         if getattr(survey, '_copy_stream', None) is None:
@@ -310,8 +317,17 @@ def _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_gr
             survey._fval = torch.zeros(1, dtype=torch.float64, device='cuda')
             survey._scratch = torch.empty(1024, dtype=torch.float64, device='cuda')
         survey._fval.zero_()
-        _lib.check(lib.b2fwi_l2_misfit(_ptr(syn), _ptr(obs_d), _ptr(dw_d), syn.numel(), _ptr(survey._res),
-                                       _ptr(survey._fval), _ptr(survey._scratch), _stream()))
+        if w1d:
+            ns, nt, nrec = syn.shape
+            if getattr(survey, '_w1d_scratch', None) is None:
+                nbytes = int(lib.b2fwi_w1d_scratch_bytes(nt, nrec, ns))
+                survey._w1d_scratch = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+            _lib.check(lib.b2fwi_w1d_misfit(_ptr(syn), _ptr(obs_d), _ptr(dw_d), nt, nrec, ns,
+                                            ctypes.c_double(float(misfit_func.gamma)), _ptr(survey._res),
+                                            _ptr(survey._fval), _ptr(survey._w1d_scratch), _stream()))
+        else:
+            _lib.check(lib.b2fwi_l2_misfit(_ptr(syn), _ptr(obs_d), _ptr(dw_d), syn.numel(), _ptr(survey._res),
+                                           _ptr(survey._fval), _ptr(survey._scratch), _stream()))
         residual = survey._res
         fval = survey._fval            # stays on the device until the all-reduce
         residuals = [LazyResidual(residual[k]) for k in range(len(shots))]

@@ -238,6 +238,16 @@ int b2fwi_window_mask_accumulate_batch(int32_t nshots, int32_t nx, int32_t nz, c
 int b2fwi_l2_misfit(const float *syn, const float *obs, const float *dw, int64_t n, float *residual_out,
                     double *fval_out, double *scratch /* >= 1024 doubles */, void *stream);
 
+/*
+ * On-device 1-D quadratic-Wasserstein misfit, trace by trace: qWasserstein(trans_type='linear', method='1d')
+ * of misfit/misfit.py:11-104 (with the direct-wave subtraction of fwi.py:146-150, dw nullable).
+ * syn, obs, dw, adjsrc_out: [nshots][nt][nrec] fp32; the positivity shift c = gamma*max(0, -min) is taken per shot
+ * record as the reference does; fval_out[0] += sum of the trace losses. scratch: b2fwi_w1d_scratch_bytes() bytes.
+ */
+int b2fwi_w1d_misfit(const float *syn, const float *obs, const float *dw, int32_t nt, int32_t nrec, int32_t nshots,
+                     double gamma, float *adjsrc_out, double *fval_out, void *scratch, void *stream);
+int64_t b2fwi_w1d_scratch_bytes(int32_t nt, int32_t nrec, int32_t nshots);
+
 #ifdef __cplusplus
 }
 #endif
