@@ -5,6 +5,7 @@
 namespace b2fwi {
 
 #define RES2D_MAX_CELLS 1024   // injection cells per CTA (shared-memory staging, double buffered)
+#define RES2D_MAX_CON 1024     // injection contributions (point, weight) per CTA, staged in shared memory
 
 struct Res2dArgs {
     // ---- decomposition (b2fwi_res2d_plan)

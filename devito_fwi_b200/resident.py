@@ -19,6 +19,7 @@ from .wavesolver import grid_struct, _ptr, _stream
 __all__ = ['ResidentSurvey', 'plan_model']
 
 MAX_CELLS = 1024      # RES2D_MAX_CELLS
+MAX_CON = 1024        # RES2D_MAX_CON (contributions per CTA; point indices are staged as uint16)
 
 
 class Plan(ctypes.Structure):
@@ -85,7 +86,7 @@ def build_maps(grid, plan, R, inj_coords, itp_coords=None):
             k = key[sel]
             cells, start = np.unique(k, return_index=True)
             ncell = cells.size
-            if ncell > MAX_CELLS:
+            if ncell > MAX_CELLS or k.size > MAX_CON or npoint > 65535:
                 return None
             inj_desc[sc] = (ncell, cell_base)
             cptr = np.concatenate([start, [k.size]]).astype(np.int32) + ncontrib
