@@ -112,8 +112,11 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     float4 dl[P];
     // per-row flags, 4 bits per row: 1 valid row, 2 inside the imaging window, 4 push to previous CTA, 8 push to next CTA
     unsigned long long flags = 0ull;
-    const float4 *Bp = reinterpret_cast<const float4 *>(a.B + (int64_t)(row0 + lr0) * a.sr + 4 * qi);
-    const int64_t Bstride = a.sr / 4;                        // row stride in float4
+    // global operands are addressed as (uniform base pointer) + 32-bit float4 index: one register per running
+    // index instead of 64-bit pointers (the kernel is register-bound)
+    const float4 *Bbase = reinterpret_cast<const float4 *>(a.B);
+    const uint32_t Bidx0 = (uint32_t)(((int64_t)(row0 + lr0) * a.sr + 4 * qi) / 4);
+    const uint32_t Bstride = (uint32_t)(a.sr / 4);           // row stride in float4
 #pragma unroll
     for (int r = 0; r < P; r++) {
         dl[r] = z4();
@@ -131,9 +134,17 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     bool push_any = false;
 #pragma unroll
     for (int r = 0; r < P; r++) push_any = push_any || (((flags >> (4 * r)) & 12ull) != 0ull);
-    const unsigned long long imask = tactive ? a.thr_mask[(int64_t)sc * T + tid] : 0ull;
-    const int ibase = tactive ? a.thr_base[(int64_t)sc * T + tid] : 0;
-
+    // injection cells owned by this thread are rare: only the row bitmap lives in a register, the lane mask and the
+    // first slot index are re-read from global memory (L1/L2) inside the rarely taken branch
+    const unsigned long long *imask_p = a.thr_mask + (int64_t)sc * T + tid;
+    const int *ibase_p = a.thr_base + (int64_t)sc * T + tid;
+    unsigned injrows = 0;                     // bit r: row r of the strip holds injection cells
+    if (tactive) {
+        const unsigned long long im = *imask_p;
+#pragma unroll
+        for (int r = 0; r < P; r++)
+            if ((im >> (4 * r)) & 0xFull) injrows |= 1u << r;
+    }
     // injection descriptors of this CTA. The (point, weight) lists never change during the sweep: they are staged
     // in shared memory once, so that the per-step gather is ONE level of independent global loads (the time
     // sample of each contributing point) instead of a three-deep dependent chain through global index arrays -
@@ -179,11 +190,13 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
 
     // history pointer of this thread's first row at the first time level; advanced by +-one slice per step
     const int64_t hq = (int64_t)(a.wq1 - a.wq0) * 4;     // history / out row stride (floats)
-    float *hptr = nullptr;
+    const uint32_t hq4 = (uint32_t)(a.wq1 - a.wq0);      // ... in float4
+    float4 *hbase = reinterpret_cast<float4 *>(a.hist);   // whole history < 2^32 float4 (64 GB): 32-bit indices
+    uint32_t hidx0 = 0;                                   // this thread's first row at the current time level
     if (a.hist)
-        hptr = a.hist + (int64_t)shot * a.hist_shot_stride + (int64_t)(t_first - a.hist_t0) * a.hist_t_stride +
-               (int64_t)(row0 + lr0 - a.wx0) * hq + 4 * (qi - a.wq0);
-    const int64_t hstep = (MODE == 0) ? a.hist_t_stride : -a.hist_t_stride;
+        hidx0 = (uint32_t)(((int64_t)shot * a.hist_shot_stride + (int64_t)(t_first - a.hist_t0) * a.hist_t_stride +
+                            (int64_t)(row0 + lr0 - a.wx0) * hq + 4 * (qi - a.wq0)) / 4);
+    const uint32_t hstep4 = (uint32_t)(((MODE == 0) ? a.hist_t_stride : -a.hist_t_stride) / 4);   // wraps mod 2^32
     const float c0 = a.c0, c0_lo = a.c0_lo, inv_dt2 = a.inv_dt2;
     const bool has_hist = a.hist != nullptr;
 
@@ -225,15 +238,15 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
             uint32_t ro = cur_s + own_off;                             // own row, current buffer
             uint32_t rn = nxt_s + own_off;                             // own row, next buffer
             uint32_t ra = acc_s0;
-            float *hp = hptr;
-            const float4 *bp = Bp;
-            opaque_ptr(bp);
+            uint32_t hp = hidx0;
+            uint32_t bp = Bidx0;
+            opaque(bp);
             float4 bpre[2], hpre[2];
-            if (flags & 0x01ull) bpre[0] = __ldg(bp);
-            if (P > 1 && (flags & 0x10ull)) bpre[1] = __ldg(bp + Bstride);
+            if (flags & 0x01ull) bpre[0] = __ldg(Bbase + bp);
+            if (P > 1 && (flags & 0x10ull)) bpre[1] = __ldg(Bbase + (bp + Bstride));
             if (MODE == 1) {
-                if (flags & 0x02ull) hpre[0] = __ldg(reinterpret_cast<const float4 *>(hp));
-                if (P > 1 && (flags & 0x20ull)) hpre[1] = __ldg(reinterpret_cast<const float4 *>(hp + hq));
+                if (flags & 0x02ull) hpre[0] = __ldg(hbase + hp);
+                if (P > 1 && (flags & 0x20ull)) hpre[1] = __ldg(hbase + (hp + hq4));
             }
 #pragma unroll
             for (int r = 0; r < P; r++) {
@@ -242,11 +255,11 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                 const unsigned f = (unsigned)(flags >> (4 * r)) & 0xFu;
                 const unsigned f2 = (r + 2 < P) ? (unsigned)(flags >> (4 * ((r + 2) & 15))) & 0xFu : 0u;
                 const float4 Bq = bpre[r & 1];
-                if (f2 & 1u) bpre[r & 1] = __ldg(bp + 2 * Bstride);
+                if (f2 & 1u) bpre[r & 1] = __ldg(Bbase + (bp + 2 * Bstride));
                 float4 hnow;
                 if (MODE == 1) {
                     hnow = hpre[r & 1];
-                    if (f2 & 2u) hpre[r & 1] = __ldg(reinterpret_cast<const float4 *>(hp + 2 * hq));
+                    if (f2 & 2u) hpre[r & 1] = __ldg(hbase + (hp + 2 * hq4));
                 }
                 if (f & 1u) {
                     const float4 Cq = w[(r + R) % NW];
@@ -278,10 +291,11 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                     const float4 den = fma4(add4(make_float4(sxr, sxr, sxr, sxr), szq), Bq, make_float4(1.f, 1.f, 1.f, 1.f));
                     const float4 c1 = make_float4(rcp_approx(den.x), rcp_approx(den.y), rcp_approx(den.z), rcp_approx(den.w));
                     float4 dn = mul4(c1, tmp);
-                    const unsigned rowbits = (unsigned)((imask >> (4 * r)) & 0xFull);
-                    if (rowbits) {
+                    if (injrows & (1u << r)) {
+                        const unsigned long long imask = __ldg(imask_p);
+                        const unsigned rowbits = (unsigned)((imask >> (4 * r)) & 0xFull);
                         const unsigned long long below = imask & ((1ull << (4 * r)) - 1ull);
-                        uint32_t sl = injc + 4u * (uint32_t)(ibase + __popcll(below));
+                        uint32_t sl = injc + 4u * (uint32_t)(__ldg(ibase_p) + __popcll(below));
                         if (rowbits & 1u) { dn.x = fmaf(lds1(sl), Bq.x, dn.x); sl += 4u; }
                         if (rowbits & 2u) { dn.y = fmaf(lds1(sl), Bq.y, dn.y); sl += 4u; }
                         if (rowbits & 4u) { dn.z = fmaf(lds1(sl), Bq.z, dn.z); sl += 4u; }
@@ -294,7 +308,7 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                             if (has_hist) {
                                 // u.dt2[t] = (delta+ - delta) / dt^2; streaming store: written once, read much later
                                 const float4 d2 = mul4s(inv_dt2, add4(dn, make_float4(-dl[r].x, -dl[r].y, -dl[r].z, -dl[r].w)));
-                                __stcs(reinterpret_cast<float4 *>(hp), d2);
+                                __stcs(hbase + hp, d2);
                             }
                             if (a.out) sts4(ra, fma4(un, un, lds4(ra)));            // illum += u[t+1]^2
                         }
@@ -304,10 +318,10 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                 ro += pitchB;
                 rn += pitchB;
                 ra += accB;
-                hp += hq;
+                hp += hq4;
                 bp += Bstride;
                 opaque(rw); opaque(ro); opaque(rn); opaque(ra);
-                opaque_ptr(hp); opaque_ptr(bp);
+                opaque(hp); opaque(bp);
             }
         }
         // push this CTA's R boundary rows into the neighbours' halo rows (distributed shared memory). Done after the
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
         { uint32_t x = cur_s; cur_s = nxt_s; nxt_s = x; }
         { uint32_t x = prv_c; prv_c = prv_n; prv_n = x; }
         { uint32_t x = nex_c; nex_c = nex_n; nex_n = x; }
-        if (hptr) hptr += hstep;
+        hidx0 += hstep4;
     }
 
     // ---- window accumulator -> global
