@@ -57,6 +57,16 @@ static __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// streaming 128-bit global load that does not allocate an L1 line: with ~219 KB of the 228 KB L1/shared array
+// used as shared memory only ~70 L1 lines are left, and allocating loads (B and history prefetches of 12 warps)
+// would serialise on them
+static __device__ __forceinline__ float4 ldg_stream4(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 static __device__ __forceinline__ void cluster_barrier()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -242,11 +252,11 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
             uint32_t bp = Bidx0;
             opaque(bp);
             float4 bpre[2], hpre[2];
-            if (flags & 0x01ull) bpre[0] = __ldg(Bbase + bp);
-            if (P > 1 && (flags & 0x10ull)) bpre[1] = __ldg(Bbase + (bp + Bstride));
+            if (flags & 0x01ull) bpre[0] = ldg_stream4(Bbase + bp);
+            if (P > 1 && (flags & 0x10ull)) bpre[1] = ldg_stream4(Bbase + (bp + Bstride));
             if (MODE == 1) {
-                if (flags & 0x02ull) hpre[0] = __ldg(hbase + hp);
-                if (P > 1 && (flags & 0x20ull)) hpre[1] = __ldg(hbase + (hp + hq4));
+                if (flags & 0x02ull) hpre[0] = ldg_stream4(hbase + hp);
+                if (P > 1 && (flags & 0x20ull)) hpre[1] = ldg_stream4(hbase + (hp + hq4));
             }
 #pragma unroll
             for (int r = 0; r < P; r++) {
@@ -255,11 +265,11 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                 const unsigned f = (unsigned)(flags >> (4 * r)) & 0xFu;
                 const unsigned f2 = (r + 2 < P) ? (unsigned)(flags >> (4 * ((r + 2) & 15))) & 0xFu : 0u;
                 const float4 Bq = bpre[r & 1];
-                if (f2 & 1u) bpre[r & 1] = __ldg(Bbase + (bp + 2 * Bstride));
+                if (f2 & 1u) bpre[r & 1] = ldg_stream4(Bbase + (bp + 2 * Bstride));
                 float4 hnow;
                 if (MODE == 1) {
                     hnow = hpre[r & 1];
-                    if (f2 & 2u) hpre[r & 1] = __ldg(hbase + (hp + 2 * hq4));
+                    if (f2 & 2u) hpre[r & 1] = ldg_stream4(hbase + (hp + 2 * hq4));
                 }
                 if (f & 1u) {
                     const float4 Cq = w[(r + R) % NW];
