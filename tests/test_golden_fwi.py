@@ -56,3 +56,25 @@ def test_cuda_objective_reproduces_reference_fwi_py(engine):
         assert abs(f - GOLD["f_loss"]) / GOLD["f_loss"] <= 1e-4 and rel_l2(g, GOLD["g_loss"]) <= 1e-4
     finally:
         fwi.ENGINE = 'auto'
+
+
+@pytest.mark.gpu
+def test_fwi_obj_single_sums_to_reference_objective():
+    """fwi_obj_single (fwi.py:131-173, per-shot API on the streaming engine): the shot sum of its (f, crop_grad, illum)
+    reproduces the reference's fwi_obj_multi golden values."""
+    from devito_fwi_b200 import fwi
+    p = problem()
+    g_true, g_init, g_const = geometries(p)
+    obs = fwi.fm_multi(g_true)
+    f_sum, g_sum, il_sum = 0., 0., 0.
+    for i in range(3):
+        f, g, res, il = fwi.fwi_obj_single(fwi._shot_geometry(g_init, i), obs[i], fwi.least_square, None,
+                                           g_init.dt, True)
+        assert g.shape == g_init.model.shape and il.shape == g.shape and res.shape == (g_init.nt, 13)
+        f_sum, g_sum, il_sum = f_sum + f, g_sum + g, il_sum + il
+    assert abs(f_sum - GOLD["f_plain"]) / GOLD["f_plain"] <= 1e-4
+    assert rel_l2(g_sum.ravel(), GOLD["g_plain"]) <= 1e-4
+    g_pre = (g_sum / np.sqrt(il_sum + 1e-30)) * p["mask"]
+    assert rel_l2(g_pre.ravel(), GOLD["g_full"]) <= 1e-4
+    f0, g0, r0, il0 = fwi.fwi_obj_single(fwi._shot_geometry(g_init, 0), obs[0], fwi.least_square, None, None, False)
+    assert g0 is None and il0 is None and f0 > 0
