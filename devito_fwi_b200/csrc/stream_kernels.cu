@@ -20,7 +20,6 @@
 namespace b2fwi {
 
 static __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-static __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 static __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 static __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 // u.dt2 from three time levels; one fixed operation order everywhere so that a checkpointed
@@ -120,9 +119,15 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
     const int64_t H = a.halo;
     // offset of this thread's float4 in plane 0
     const int64_t own0 = (NDIM == 3 ? H * a.sp : 0) + (int64_t)(r + H) * a.sr + (z0 + H);
+    // every global operand is addressed as (uniform base) + 32-bit float4 index: a slice has < 2^32 float4
+    // (one IMAD.WIDE per access instead of 64-bit add chains; the kernel is issue-sensitive)
+    const uint32_t own4 = (uint32_t)(own0 >> 2);
+    const uint32_t sp4 = (uint32_t)(a.sp >> 2);
+#define F4(ptr) reinterpret_cast<const float4 *>(ptr)
+#define F4W(ptr) reinterpret_cast<float4 *>(ptr)
 
     // ---- halo work items of this thread (fixed across planes)
-    int64_t hoff[NH];      // global offset inside plane 0, or -1
+    uint32_t hoff[NH];     // float4 index inside plane 0, or 0xffffffff
     int hsm[NH];           // shared offset (floats) inside one buffer, or -1
 #pragma unroll
     for (int i = 0; i < NH; i++) {
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
         hsm[i] = (srow >= 0) ? srow * SW + scol : -1;
         const int gr = r0 - R + srow;
         const bool ok = (srow >= 0) && gr >= 0 && gr < a.nr && gz >= 0 && gz < a.nz;
-        hoff[i] = ok ? (NDIM == 3 ? H * a.sp : 0) + (int64_t)(gr + H) * a.sr + (gz + H) : -1;
+        hoff[i] = ok ? (uint32_t)(((NDIM == 3 ? H * a.sp : 0) + (int64_t)(gr + H) * a.sr + (gz + H)) >> 2) : 0xffffffffu;
     }
 
     // undamped interior (coef[0] == 1 exactly): this thread never reads c1 for planes inside the box
@@ -158,20 +163,20 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
 #pragma unroll
         for (int i = 0; i < NQ; i++) {
             const int p = p_begin - R + i;
-            q[i] = (active && p >= 0 && p < a.np) ? ld4(a.cur + own0 + (int64_t)p * a.sp) : zero4();
+            q[i] = (active && p >= 0 && p < a.np) ? F4(a.cur)[own4 + (uint32_t)p * sp4] : zero4();
         }
     } else {
-        q[0] = active ? ld4(a.cur + own0) : zero4();
+        q[0] = active ? F4(a.cur)[own4] : zero4();
     }
     float4 hreg[NH];
 #pragma unroll
     for (int i = 0; i < NH; i++)
-        hreg[i] = (hoff[i] >= 0) ? ld4(a.cur + hoff[i] + (int64_t)p_begin * (NDIM == 3 ? a.sp : 0)) : zero4();
+        hreg[i] = (hoff[i] != 0xffffffffu) ? F4(a.cur)[hoff[i] + (NDIM == 3 ? (uint32_t)p_begin * sp4 : 0u)] : zero4();
 
     // plane loop; for R <= 4 it is unrolled NQ times so that the register pipeline rotates through
     // compile-time slots instead of being shifted (2R float4 moves per plane otherwise)
     constexpr int UNR = (NDIM == 3 && R <= 4) ? NQ : 1;
-    int64_t pofs_run = (NDIM == 3) ? (int64_t)p_begin * a.sp : 0;      // plane offset, advanced by one plane per iteration
+    uint32_t pofs_run = (NDIM == 3) ? (uint32_t)p_begin * sp4 : 0u;    // plane offset (float4), advanced by one plane per iteration
     for (int pb = p_begin; pb < p_end; pb += UNR) {
 #pragma unroll
         for (int j = 0; j < UNR; j++) {
@@ -179,8 +184,9 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
             if (p < p_end) {
                 const int buf = (p - p_begin) & 1;
                 float *tb = &tile[buf][0][0];
-                const int64_t pofs = pofs_run;
-                pofs_run += a.sp;
+                const uint32_t pofs = pofs_run;
+                const uint32_t idx = own4 + pofs;
+                pofs_run += sp4;
                 // stage plane p
                 st4(tb + (R + tr) * SW + ZH + 4 * tz, q[(j + QC) % NQ]);
 #pragma unroll
@@ -190,38 +196,38 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
                 // pointwise operands of plane p
                 float4 prev, c1, c2, g4, h0, h1, h2, il;      // only defined (and only used) by active threads
                 if (active) {
-                    prev = ld4(a.prev + own0 + pofs);
-                    c1 = (in_box && p >= blo_p && p < bhi_p) ? one4 : ldg4(a.c1 + own0 + pofs);
-                    c2 = ldg4(a.c2 + own0 + pofs);
+                    prev = F4(a.prev)[idx];
+                    c1 = (in_box && p >= blo_p && p < bhi_p) ? one4 : __ldg(F4(a.c1) + idx);
+                    c2 = __ldg(F4(a.c2) + idx);
                     if (IMG != 0) {
-                        g4 = ld4(a.grad + own0 + pofs);
-                        h1 = ldg4(a.h1 + own0 + pofs);
+                        g4 = F4(a.grad)[idx];
+                        h1 = __ldg(F4(a.h1) + idx);
                         if (IMG == 1) {
-                            h0 = ldg4(a.h0 + own0 + pofs);
-                            h2 = ldg4(a.h2 + own0 + pofs);
+                            h0 = __ldg(F4(a.h0) + idx);
+                            h2 = __ldg(F4(a.h2) + idx);
                         }
                     }
-                    if (a.illum) il = ld4(a.illum + own0 + pofs);
+                    if (a.illum) il = F4(a.illum)[idx];
                 }
                 // prefetch for plane p+1
                 float4 qn = zero4();
                 if (p + 1 < p_end) {
                     if (NDIM == 3) {
                         const int pn = p + R + 1;
-                        if (active && pn < a.np) qn = ld4(a.cur + own0 + pofs + (int64_t)(R + 1) * a.sp);
+                        if (active && pn < a.np) qn = F4(a.cur)[idx + (uint32_t)(R + 1) * sp4];
                     }
 #pragma unroll
                     for (int i = 0; i < NH; i++)
-                        hreg[i] = (hoff[i] >= 0) ? ld4(a.cur + hoff[i] + pofs + a.sp) : zero4();
+                        hreg[i] = (hoff[i] != 0xffffffffu) ? F4(a.cur)[hoff[i] + pofs + sp4] : zero4();
                 }
                 __syncthreads();
 
                 if (active) {
                     const float4 C = q[(j + QC) % NQ];
                     const float4 o = point_update<R, NDIM, SW>(a, q, j, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, zvalid);
-                    st4(a.out + own0 + pofs, o);
-                    if (IMG != 0) st4(a.grad + own0 + pofs, img4(g4, IMG == 1 ? d2u4(h0, h1, h2, a.inv_dt2) : h1, C));
-                    if (a.illum) st4(a.illum + own0 + pofs, fma4(C, C, il));
+                    F4W(a.out)[idx] = o;
+                    if (IMG != 0) F4W(a.grad)[idx] = img4(g4, IMG == 1 ? d2u4(h0, h1, h2, a.inv_dt2) : h1, C);
+                    if (a.illum) F4W(a.illum)[idx] = fma4(C, C, il);
                     if (a.d2u) {
                         float4 d = d2u4(prev, C, o, a.inv_dt2);
                         if (zvalid < 4) {
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
                             if (zvalid < 3) d.z = 0.f;
                             d.w = 0.f;
                         }
-                        st4(a.d2u + own0 + pofs, d);
+                        F4W(a.d2u)[idx] = d;
                     }
                 }
                 if (NDIM == 3) {
@@ -245,6 +251,8 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
         }
     }
 }
+#undef F4
+#undef F4W
 
 // ------------------------------------------------------------------------------------------------
 // 3-D variant with an asynchronous-copy pipeline (cp.async, three stages): the halo of plane p+2 goes
