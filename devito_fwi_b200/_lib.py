@@ -51,17 +51,33 @@ def needs_build():
 
 
 def build(verbose=False, force=False):
-    """Compile csrc/*.cu for sm_100a into devito_fwi_b200/libb2fwi.so (in-tree)."""
+    """Compile csrc/*.cu for sm_100a into devito_fwi_b200/libb2fwi.so (in-tree): one nvcc -c per source in
+    parallel, then one link step."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + sources()
+    import tempfile
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if res.returncode != 0:
-        raise B2fwiError("nvcc failed:\n" + res.stdout)
-    if verbose:
-        print(res.stdout)
+        flags = ["-Xptxas=-v"] + flags
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = []
+        for src in sources():
+            obj = os.path.join(tmp, os.path.basename(src)[:-3] + ".o")
+            cmd = ["nvcc"] + flags + ["-c", "-o", obj, src]
+            procs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs, log = [], ""
+        for obj, pr in procs:
+            out, _ = pr.communicate()
+            log += out
+            if pr.returncode != 0:
+                raise B2fwiError("nvcc failed:\n" + log)
+            objs.append(obj)
+        res = subprocess.run(["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + objs, stdout=subprocess.PIPE,
+                             stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            raise B2fwiError("nvcc link failed:\n" + res.stdout)
+        if verbose:
+            print(log + res.stdout)
     return LIB_PATH
 
 
