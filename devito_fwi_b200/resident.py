@@ -46,6 +46,28 @@ def plan_model(grid, space_order, nbl, min_cluster=1):
     return plan if rc == 0 else None
 
 
+def choose_plan(grid, space_order, nbl, nshots):
+    """Cluster size for `nshots` concurrent shots: among the feasible decompositions pick the one that
+    minimises (waves of resident clusters) x (rows per CTA) -- few shots get more SMs each, many shots the
+    smallest cluster that fits. Uses cudaOccupancyMaxActiveClusters through the C ABI."""
+    g = grid_struct(grid, space_order)
+    best, best_cost, seen = None, None, set()
+    for cmin in range(1, 9):
+        plan = plan_model(grid, space_order, nbl, cmin)
+        if plan is None or plan.cluster in seen:
+            continue
+        seen.add(plan.cluster)
+        n = ctypes.c_int32()
+        rc = _lib.lib().b2fwi_res2d_max_active_clusters(ctypes.byref(g), ctypes.byref(plan), ctypes.byref(n))
+        if rc != 0 or n.value <= 0:
+            continue
+        waves = -(-nshots // n.value)
+        cost = waves * plan.rows_cta * (1.0 + 0.02 * plan.cluster)       # mild penalty: wider barrier
+        if best is None or cost < best_cost:
+            best, best_cost = plan, cost
+    return best
+
+
 def build_maps(grid, plan, R, inj_coords, itp_coords=None):
     """numpy arrays of struct b2fwi_res2d_maps for a list of shots.
 
@@ -166,7 +188,8 @@ class ResidentSurvey(object):
         self.R = self.space_order // 2
         self.shots = list(range(geometry.nsrc)) if shots is None else list(shots)
         self.nshots = len(self.shots)
-        self.plan = plan_model(self.grid, self.space_order, model.nbl, min_cluster)
+        self.plan = (choose_plan(self.grid, self.space_order, model.nbl, self.nshots) if min_cluster == 1
+                     else plan_model(self.grid, self.space_order, model.nbl, min_cluster))
         if self.plan is None or not self.supported(geometry, self.space_order):
             raise ValueError("model does not fit the SM-resident engine")
         self.nt = geometry.nt

@@ -134,8 +134,10 @@ def test_resident_many_shots_small_grid_vs_streaming():
     src = np.stack([np.linspace(-50., 1240., nsrc), np.full(nsrc, 25.)], axis=1)      # first / last in the sponge
     rec = np.stack([np.linspace(-300., 1500., 37), np.full(37, 33.3)], axis=1)        # first / last outside the grid
     geom = b.AcquisitionGeometry(model, rec, src, 0., 420., f0=0.02, src_type='Ricker')
-    sv = ResidentSurvey(geom)
+    sv = ResidentSurvey(geom, min_cluster=2)          # a 2-CTA cluster: exercises the DSMEM halo exchange on both sides
     assert sv.plan.cluster == 2
+    from devito_fwi_b200.resident import choose_plan
+    assert choose_plan(model.grid, so, nbl, nsrc).cluster >= 2
     syn = sv.forward(save=True, illum=True).clone()
     g_res = sv.crop(sv.gradient(syn.contiguous())).cpu().numpy()
     il_res = sv.crop(sv.illum).cpu().numpy()
