@@ -230,3 +230,20 @@ def test_marmousi_fwi_example_reduces_the_objective():
         sys.argv = argv
     assert len(history) >= 3
     assert min(history) < 0.8 * history[0]
+
+
+def test_observed_data_cache_follows_host_modifications():
+    """The device copy of the observed records is re-used between evaluations, but any access to a record's
+    host view (obs[i].data - the caller may have changed it) forces a fresh upload."""
+    from devito_fwi_b200 import configs, fwi
+    g_true, g_init = configs.circle(space_order=4, nsrc=2)
+    obs = fwi.fm_multi(g_true)
+    f1, _, _ = fwi.fwi_obj_multi(g_init, obs, fwi.least_square, None, None, False, False)
+    f1b, _, _ = fwi.fwi_obj_multi(g_init, obs, fwi.least_square, None, None, False, False)
+    assert f1 == f1b
+    obs[0].data[:] = 0.0                         # in-place host modification
+    f2, _, _ = fwi.fwi_obj_multi(g_init, obs, fwi.least_square, None, None, False, False)
+    assert f2 != f1
+    obs2 = fwi.fm_multi(g_true)                  # a different list object with the original data
+    f3, _, _ = fwi.fwi_obj_multi(g_init, obs2, fwi.least_square, None, None, False, False)
+    assert np.isclose(f3, f1, rtol=1e-12)
