@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libb2fwi.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "stream_kernels.cu", "resident2d.cu", "res2d_api.cu"]
+SOURCES = ["api.cu", "stream_kernels.cu", "stream_tma.cu", "resident2d.cu", "res2d_api.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(_ROOT, "include")]

@@ -16,79 +16,9 @@
 #include "common.cuh"
 #include "packed.cuh"
 #include "stream_kernels.cuh"
+#include "stream_point.cuh"
 
 namespace b2fwi {
-
-static __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-static __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
-static __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-// u.dt2 from three time levels; one fixed operation order everywhere so that a checkpointed
-// gradient (u.dt2 stored by the recompute sweep) is bitwise identical to the full-history one.
-static __device__ __forceinline__ float d2u_of(float um, float uc, float up, float inv_dt2)
-{
-    return __fmul_rn(__fadd_rn(__fmaf_rn(-2.f, uc, um), up), inv_dt2);
-}
-
-// The point update shared by all streaming kernels (identical arithmetic => identical results whichever
-// kernel variant computes a sweep): packed fp32x2, three independent accumulation chains.
-//   q[0..NQ-1]: register pipeline along the plane axis (centre at QC); ctr: this thread's float4 in the staged tile.
-//   The pipeline is addressed circularly: plane offset i in -R..R lives in q[(j + R + i) % NQ] (j: rotation).
-template <int R, int NDIM, int SW>
-static __device__ __forceinline__ float4 point_update(const StepArgs &a, const float4 *q, int j, const float *ctr,
-                                                     float4 prev, float4 c1, float4 c2, int zvalid)
-{
-    constexpr int RZ4 = (R + 3) / 4, ZH = 4 * RZ4;
-    constexpr int NQ = (NDIM == 3) ? 2 * R + 1 : 1;
-    constexpr int QC = (NDIM == 3) ? R : 0;
-    const float4 C = q[(j + QC) % NQ];
-    float4 lp = fma4s(a.c0, C, mul4s(a.c0_lo, C));          // centre weight as exact hi + lo (see api.cu)
-    if (NDIM == 3) {
-#pragma unroll
-        for (int k = 1; k <= R; k++) lp = fma4s(a.cp[k], add4(q[(j + QC + k) % NQ], q[(j + QC - k + NQ) % NQ]), lp);
-    }
-    float4 lr = mul4s(a.cr[1], add4(ld4(ctr + SW), ld4(ctr - SW)));
-#pragma unroll
-    for (int k = 2; k <= R; k++) lr = fma4s(a.cr[k], add4(ld4(ctr + k * SW), ld4(ctr - k * SW)), lr);
-    float zl[ZH + 4 + ZH];
-#pragma unroll
-    for (int i = 0; i < RZ4; i++) {
-        const float4 Lq = ld4(ctr - ZH + 4 * i), Rq = ld4(ctr + 4 + 4 * i);
-        zl[4 * i + 0] = Lq.x; zl[4 * i + 1] = Lq.y; zl[4 * i + 2] = Lq.z; zl[4 * i + 3] = Lq.w;
-        zl[ZH + 4 + 4 * i + 0] = Rq.x; zl[ZH + 4 + 4 * i + 1] = Rq.y;
-        zl[ZH + 4 + 4 * i + 2] = Rq.z; zl[ZH + 4 + 4 * i + 3] = Rq.w;
-    }
-    zl[ZH + 0] = C.x; zl[ZH + 1] = C.y; zl[ZH + 2] = C.z; zl[ZH + 3] = C.w;
-    const float2 c1k = make_float2(a.cz[1], a.cz[1]);
-    float2 l01 = __fmul2_rn(c1k, __fadd2_rn(make_float2(zl[ZH + 1], zl[ZH + 2]), make_float2(zl[ZH - 1], zl[ZH])));
-    float2 l23 = __fmul2_rn(c1k, __fadd2_rn(make_float2(zl[ZH + 3], zl[ZH + 4]), make_float2(zl[ZH + 1], zl[ZH + 2])));
-#pragma unroll
-    for (int k = 2; k <= R; k++) {
-        const float2 ck = make_float2(a.cz[k], a.cz[k]);
-        l01 = __ffma2_rn(ck, __fadd2_rn(make_float2(zl[ZH + k], zl[ZH + 1 + k]), make_float2(zl[ZH - k], zl[ZH + 1 - k])), l01);
-        l23 = __ffma2_rn(ck, __fadd2_rn(make_float2(zl[ZH + 2 + k], zl[ZH + 3 + k]),
-                                        make_float2(zl[ZH + 2 - k], zl[ZH + 3 - k])), l23);
-    }
-    const float4 lap = add4(add4(lp, lr), mk4(l01, l23));
-    // u+ = u + c1 (u - u-) + c2 L(u)
-    const float4 t = fma4(c1, add4(C, make_float4(-prev.x, -prev.y, -prev.z, -prev.w)), C);
-    float4 o = fma4(c2, lap, t);
-    if (zvalid < 4) {                     // only the last, partial quad of a row: keep the pitch padding zero
-        if (zvalid < 2) o.y = 0.f;
-        if (zvalid < 3) o.z = 0.f;
-        o.w = 0.f;
-    }
-    return o;
-}
-
-// packed forms of d2u_of / the imaging update (FFMA2 etc. round exactly like their scalar counterparts)
-static __device__ __forceinline__ float4 d2u4(float4 um, float4 uc, float4 up, float inv_dt2)
-{
-    return mul4s(inv_dt2, add4(fma4s(-2.f, uc, um), up));
-}
-static __device__ __forceinline__ float4 img4(float4 g, float4 d2, float4 v)     // grad += -u.dt2 * v
-{
-    return fma4(make_float4(-d2.x, -d2.y, -d2.z, -d2.w), v, g);
-}
 
 // TZQ x TR: tile shape in float4 columns x rows (threads = TZQ*TR); MINB: minimum resident CTAs per SM.
 template <int R, int NDIM, int IMG, int MINB, int TZQ = 16, int TR = 16>
@@ -482,6 +412,7 @@ int launch_step(const Layout &L, StepArgs a, int img, cudaStream_t st)
 {
     a.np = L.np; a.nr = L.nr; a.nz = L.nz; a.halo = L.halo; a.sp = L.sp; a.sr = L.sr;
     if (a.chunk <= 0) a.chunk = pick_chunk(L);
+    if (tma_step_supported(L, a, img)) return launch_step_tma(L, a, st);
     const int nchunks = (L.ndim == 3) ? (L.np + a.chunk - 1) / a.chunk : 1;
     int tzc, trc, bps;
     tile_shape(L.ndim, &tzc, &trc, &bps);
