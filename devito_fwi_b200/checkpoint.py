@@ -11,6 +11,10 @@ fit in HBM (3-D models).  Replaces pyrevolve / examples.checkpointing of the ref
 The forward kernels are deterministic, so the recomputed wavefield - and therefore the gradient -
 is bitwise identical to the one obtained from a full saved history (tests/test_gpu_parity.py).
 S ~ sqrt(2 * steps) minimises (2 * n_segments + S) slices of HBM.
+
+``forward(save='checkpoint')`` runs pass 1 while it records the receivers, and ``gradient(rec, u=<its result>)``
+then only needs pass 2: forward + recompute + adjoint = 3 sweeps per shot gradient instead of the 4 of the
+reference's call sequence (forward for the data, then forward + reverse inside the Revolver).
 """
 import ctypes
 import math
@@ -18,7 +22,7 @@ import math
 from . import _lib
 from .sparse import sparse_map
 
-__all__ = ['checkpointed_gradient', 'plan_segments']
+__all__ = ['checkpointed_gradient', 'checkpointed_forward', 'CheckpointedWavefield', 'plan_segments']
 
 
 def plan_segments(time_m, time_M, segment=None):
@@ -29,13 +33,30 @@ def plan_segments(time_m, time_M, segment=None):
     return [(ta, min(ta + S - 1, time_M)) for ta in range(time_m, time_M + 1, S)]
 
 
-def checkpointed_gradient(solver, rec, v, grad, vp, dt, **kwargs):
-    """Gradient with checkpointing; same results as ``jacobian_adjoint(rec, u_saved)``."""
+class CheckpointedWavefield(object):
+    """What ``AcousticWaveSolver.forward(save='checkpoint')`` returns in place of a saved TimeFunction:
+    the checkpoints of pass 1 (two slices per segment) and u.dt2 of the last segment, so that
+    ``gradient(rec, u=<this>)`` goes straight to pass 2 - the forward sweep that produced the synthetic
+    data is not repeated (the reference's pyrevolve branch runs it a second time, wavesolver.py:188-201)."""
+    save = None
+
+    def __init__(self, solver, src, vp_dev, coef, dt, nt, time_m, time_M, segs, ring, ckpt, segbuf):
+        self.solver, self.src, self.vp_dev, self.coef, self.dt = solver, src, vp_dev, coef, dt
+        self.nt, self.time_m, self.time_M, self.segs = nt, time_m, time_M, segs
+        self.ring, self.ckpt, self.segbuf = ring, ckpt, segbuf
+
+    @property
+    def nbytes(self):
+        return sum(t.numel() * 4 for t in (self.ring, self.ckpt, self.segbuf))
+
+
+def checkpointed_forward(solver, src, rec, vp, dt, illum=None, **kwargs):
+    """Pass 1: forward sweep on a 3-slot ring with receiver recording (and the source illumination),
+    checkpointing the two live slices before every segment. Returns a CheckpointedWavefield."""
     import torch
-    from .wavesolver import _ptr, _stream, _Timer, BYTES_ADJ, BYTES_FWD
+    from .wavesolver import _ptr, _stream
     lib = _lib.lib()
-    src = kwargs.pop('src', None) or solver.geometry.src
-    nt = min(rec.nt, src.nt)
+    nt = min(rec.nt, src.nt) if rec is not None else src.nt
     time_m, time_M = solver._time_bounds(kwargs, nt)
     segs = plan_segments(time_m, time_M, kwargs.pop('segment', None))
     grid = solver.model.grid
@@ -43,11 +64,10 @@ def checkpointed_gradient(solver, rec, v, grad, vp, dt, **kwargs):
     vp_dev = solver._vp_dev(vp)
     coef = solver._coeffs(vp_dev, dt)
     src_map = sparse_map(grid, src.coordinates.data)
-    rec_map = sparse_map(grid, rec.coordinates.data)
     src_dev = src._sdata.dev()
-    rec_dev = rec._sdata.dev()
-    v_dev = v._buf.dev(write=True)
-    grad_dev = grad._buf.dev(write=True)
+    rec_map = sparse_map(grid, rec.coordinates.data) if rec is not None else None
+    rec_dev = rec._sdata.dev(write=True) if rec is not None else None
+    illum_dev = illum._buf.dev(write=True) if illum is not None else None
     slice_shape = grid.slice_shape
     ring = torch.zeros((3,) + slice_shape, dtype=torch.float32, device='cuda')
     nseg = len(segs)
@@ -55,27 +75,54 @@ def checkpointed_gradient(solver, rec, v, grad, vp, dt, **kwargs):
     ckpt = torch.empty((max(nseg, 1), 2) + slice_shape, dtype=torch.float32, device='cuda')
     segbuf = torch.empty((S,) + slice_shape, dtype=torch.float32, device='cuda')
     cdt = ctypes.c_float(dt)
-    timer = _Timer(solver._profile)
-
-    def fwd(ta, tb, d2u):
-        _lib.check(lib.b2fwi_forward(
-            ctypes.byref(g), _ptr(vp_dev), _ptr(coef), cdt, nt, ta, tb,
-            _ptr(src_dev), src_map.byref(), None, None, _ptr(ring), 0, None,
-            _ptr(segbuf) if d2u else None, ta, _stream()))
-
     for k, (ta, tb) in enumerate(segs):
         ckpt[k, 0].copy_(ring[(ta - 1) % 3])
         ckpt[k, 1].copy_(ring[ta % 3])
-        fwd(ta, tb, d2u=(k == nseg - 1))
+        _lib.check(lib.b2fwi_forward(
+            ctypes.byref(g), _ptr(vp_dev), _ptr(coef), cdt, nt, ta, tb,
+            _ptr(src_dev), src_map.byref(), _ptr(rec_dev), rec_map.byref() if rec_map is not None else None,
+            _ptr(ring), 0, _ptr(illum_dev), _ptr(segbuf) if k == nseg - 1 else None, ta, _stream()))
+    return CheckpointedWavefield(solver, src, vp_dev, coef, dt, nt, time_m, time_M, segs, ring, ckpt, segbuf)
+
+
+def checkpointed_gradient(solver, rec, v, grad, vp, dt, checkpoints=None, **kwargs):
+    """Gradient with checkpointing; same results as ``jacobian_adjoint(rec, u_saved)``.
+    ``checkpoints``: the CheckpointedWavefield of an earlier ``forward(save='checkpoint')`` with the same
+    model; without it pass 1 is run here (the reference's behaviour)."""
+    from .wavesolver import _ptr, _stream, _Timer, BYTES_ADJ, BYTES_FWD
+    lib = _lib.lib()
+    timer = _Timer(solver._profile)
+    cw = checkpoints
+    if cw is None:
+        src = kwargs.pop('src', None) or solver.geometry.src
+        nt_ = min(rec.nt, src.nt)
+        tm, tM = solver._time_bounds(kwargs, nt_)
+        cw = checkpointed_forward(solver, src, None, vp, dt, time_m=tm, time_M=tM, segment=kwargs.pop('segment', None))
+        cw.nt = nt_
+    nt, segs, ring, ckpt, segbuf = cw.nt, cw.segs, cw.ring, cw.ckpt, cw.segbuf
+    grid = solver.model.grid
+    g = solver._gs()
+    vp_dev, coef, src = cw.vp_dev, cw.coef, cw.src
+    src_map = sparse_map(grid, src.coordinates.data)
+    rec_map = sparse_map(grid, rec.coordinates.data)
+    src_dev = src._sdata.dev()
+    rec_dev = rec._sdata.dev()
+    v_dev = v._buf.dev(write=True)
+    grad_dev = grad._buf.dev(write=True)
+    nseg = len(segs)
+    cdt = ctypes.c_float(cw.dt)
     for k in range(nseg - 1, -1, -1):
         ta, tb = segs[k]
         if k != nseg - 1:
             ring[(ta - 1) % 3].copy_(ckpt[k, 0])
             ring[ta % 3].copy_(ckpt[k, 1])
-            fwd(ta, tb, d2u=True)
+            _lib.check(lib.b2fwi_forward(
+                ctypes.byref(g), _ptr(vp_dev), _ptr(coef), cdt, nt, ta, tb,
+                _ptr(src_dev), src_map.byref(), None, None, _ptr(ring), 0, None, _ptr(segbuf), ta, _stream()))
         _lib.check(lib.b2fwi_gradient(
             ctypes.byref(g), _ptr(vp_dev), _ptr(coef), cdt, nt, ta, tb,
             _ptr(rec_dev), rec_map.byref(), _ptr(segbuf), 2, ta, _ptr(v_dev), _ptr(grad_dev), _stream()))
-    steps = max(time_M - time_m + 1, 0)
-    summary = solver._summary('Gradient', timer.stop(), steps, BYTES_ADJ + 2 * BYTES_FWD)
+    steps = max(cw.time_M - cw.time_m + 1, 0)
+    bpp = BYTES_ADJ + (1 if checkpoints is not None else 2) * BYTES_FWD
+    summary = solver._summary('Gradient', timer.stop(), steps, bpp)
     return grad, summary

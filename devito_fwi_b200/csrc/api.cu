@@ -172,7 +172,7 @@ int b2fwi_forward(const b2fwi_grid *g, const float *vp, const float *coef, float
             return rc;
         if (nrec > 0 && (rc = launch_interp(uc, rec + (int64_t)time * nrec, rec_map, st))) return rc;
     }
-    if (illum && time_m <= time_M) {
+    if (illum && time_m <= time_M && time_M == nt - 2) {     // the call producing the last slice adds it
         const int64_t sl = save ? time_M + 1 : (time_M + 1) % 3;
         if ((rc = launch_accum_sq(L, illum, u + sl * L.elems, st))) return rc;
     }

@@ -412,7 +412,7 @@ int launch_step(const Layout &L, StepArgs a, int img, cudaStream_t st)
 {
     a.np = L.np; a.nr = L.nr; a.nz = L.nz; a.halo = L.halo; a.sp = L.sp; a.sr = L.sr;
     if (a.chunk <= 0) a.chunk = pick_chunk(L);
-    if (tma_step_supported(L, a, img)) return launch_step_tma(L, a, st);
+    if (tma_step_supported(L, a, img)) return launch_step_tma(L, a, img, st);
     const int nchunks = (L.ndim == 3) ? (L.np + a.chunk - 1) / a.chunk : 1;
     int tzc, trc, bps;
     tile_shape(L.ndim, &tzc, &trc, &bps);

@@ -28,9 +28,9 @@ struct StepArgs {
 void fill_stencil_weights(const Layout &L, StepArgs *a);
 int pick_chunk(const Layout &L);
 int launch_step(const Layout &L, StepArgs a, int img, cudaStream_t st);
-// TMA-staged 3-D forward sweep (stream_tma.cu)
+// TMA-staged 3-D sweeps: forward, adjoint + imaging from u.dt2 (stream_tma.cu)
 bool tma_step_supported(const Layout &L, const StepArgs &a, int img);
-int launch_step_tma(const Layout &L, const StepArgs &a, cudaStream_t st);
+int launch_step_tma(const Layout &L, const StepArgs &a, int img, cudaStream_t st);
 int launch_inject(float *field, const float *vp, float dt, const float *vals, const b2fwi_sparse *m,
                   float *d2u, const float *cur, const float *prev, float inv_dt2, cudaStream_t st);
 int launch_interp(const float *field, float *out, const b2fwi_sparse *m, cudaStream_t st);

@@ -69,13 +69,14 @@ static __device__ __forceinline__ float4 lds4(uint32_t addr)
     return v;
 }
 
-template <int R, int NPCC>
+template <int R, int NPCC, int IMG>
 struct TmaCfg {
     static constexpr int TZQ = 32, TR = 16, TZ = 4 * TZQ, ZH = 4, SW = TZ + 2 * ZH, SROWS = TR + 2 * R;
     static constexpr int NQ = 2 * R + 1, NCUR = NQ;
     static constexpr int CUR_BYTES = SROWS * SW * 4;       // one u[t] box
     static constexpr int PL_BYTES = TR * TZ * 4;           // one pointwise-operand box
-    static constexpr int PCC_BYTES = 3 * PL_BYTES;         // prev, c2, c1
+    static constexpr int NARR = (IMG == 2) ? 4 : 3;        // prev, c2, c1 [, u.dt2]
+    static constexpr int PCC_BYTES = NARR * PL_BYTES;
     static constexpr int NCONS = TZQ * TR, NTHREADS = NCONS + 32;
     static constexpr int BAR_OFF = NCUR * CUR_BYTES + NPCC * PCC_BYTES;     // mbarriers (64 slots reserved)
     static constexpr int W_OFF = BAR_OFF + 64 * 8;                          // Laplacian weights, 32 floats
@@ -87,13 +88,14 @@ struct TmaCfg {
     static_assert(2 * NCUR + NPCC <= 64, "barrier slots");
 };
 
-template <int R, int NPCC, bool EXTRAS>
-__global__ void __launch_bounds__(TmaCfg<R, NPCC>::NTHREADS, 1)
+// IMG: 0 forward sweep (EXTRAS: illumination / u.dt2 store), 2 adjoint sweep + imaging from stored u.dt2.
+template <int R, int NPCC, int IMG, bool EXTRAS>
+__global__ void __launch_bounds__(TmaCfg<R, NPCC, IMG>::NTHREADS, 1)
 step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CUtensorMap m_cur,
                   const __grid_constant__ CUtensorMap m_prev, const __grid_constant__ CUtensorMap m_c1,
-                  const __grid_constant__ CUtensorMap m_c2)
+                  const __grid_constant__ CUtensorMap m_c2, const __grid_constant__ CUtensorMap m_h1)
 {
-    using C = TmaCfg<R, NPCC>;
+    using C = TmaCfg<R, NPCC, IMG>;
     constexpr int TZ = C::TZ, TR = C::TR, ZH = C::ZH, SW = C::SW, NQ = C::NQ, NCUR = C::NCUR;
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -156,10 +158,11 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
                 const bool skip_c1 = p >= blo_p && p < bhi_p;
                 const uint32_t bar = full_p + 8 * (k % NPCC);
                 const uint32_t dst = pcc_s + (k % NPCC) * C::PCC_BYTES;
-                mbar_expect_tx(bar, skip_c1 ? 2 * C::PL_BYTES : 3 * C::PL_BYTES);
+                mbar_expect_tx(bar, (skip_c1 ? C::NARR - 1 : C::NARR) * C::PL_BYTES);
                 tma_load_3d(dst, &m_prev, bar, ztile0, r0, p);
                 tma_load_3d(dst + C::PL_BYTES, &m_c2, bar, ztile0, r0, p);
                 if (!skip_c1) tma_load_3d(dst + 2 * C::PL_BYTES, &m_c1, bar, ztile0, r0, p);
+                if (IMG == 2) tma_load_3d(dst + 3 * C::PL_BYTES, &m_h1, bar, ztile0, r0, p);
             };
             // fill both rings, in the order the planes are needed
             for (int k = 0; k < NCUR; k++) {
@@ -228,6 +231,10 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
         for (int j = 0; j < NQ; j++) {
             const int i = pb + j;
             if (!EDGE || i < n_it) {
+                float4 g4;
+                // imaging: grad goes through registers (the operand ring has no room for a fifth array); the load
+                // is issued before the barrier waits and consumed after the update
+                if (IMG == 2 && active) g4 = F4(a.grad)[idx];
                 // feed: plane i+R enters the register pipeline from its ring stage
                 const int sf = (j + R) % NQ;
                 if (!EDGE || i + R < ncur) {
@@ -243,6 +250,8 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
                 const float4 prev = lds4(pcc_t + sp * C::PCC_BYTES);
                 const float4 c2 = lds4(pcc_t + sp * C::PCC_BYTES + C::PL_BYTES);
                 const float4 c1 = (p >= blo_p && p < bhi_p) ? one4 : lds4(pcc_t + sp * C::PCC_BYTES + 2 * C::PL_BYTES);
+                float4 h1;
+                if (IMG == 2) h1 = lds4(pcc_t + sp * C::PCC_BYTES + 3 * C::PL_BYTES);
                 // no z masking: beyond nz the TMA unit filled u[t], u[t-1] and c2 with zeros, so o == 0 there
                 const float4 o = point_update<R, 3, SW, false>(w, q, j, SAddr{ctr_s + (j % NCUR) * C::CUR_BYTES},
                                                                prev, c1, c2, 4);
@@ -251,6 +260,7 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
                 if (lane0) mbar_arrive(bar_em + 8 * (j % NCUR));
                 if (active) {
                     F4W(a.out)[idx] = o;
+                    if (IMG == 2) F4W(a.grad)[idx] = img4(g4, h1, q[(j + R) % NQ]);
                     if (EXTRAS) {
                         const float4 Cc = q[(j + R) % NQ];
                         if (a.illum) F4W(a.illum)[idx] = fma4(Cc, Cc, F4(a.illum)[idx]);
@@ -304,35 +314,40 @@ static int make_map(CUtensorMap *m, const float *field, const StepArgs &a, int b
     return 0;
 }
 
-template <int R, int NPCC, bool EXTRAS>
+template <int R, int NPCC, int IMG, bool EXTRAS>
 static int launch_tma(const StepArgs &a, cudaStream_t st)
 {
-    using C = TmaCfg<R, NPCC>;
-    auto kern = step3d_tma_kernel<R, NPCC, EXTRAS>;
+    using C = TmaCfg<R, NPCC, IMG>;
+    static_assert(C::SMEM <= 232448, "shared memory per CTA");
+    auto kern = step3d_tma_kernel<R, NPCC, IMG, EXTRAS>;
     static bool configured = false;
     if (!configured) {
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
     }
-    CUtensorMap m_cur, m_prev, m_c1, m_c2;
+    CUtensorMap m_cur, m_prev, m_c1, m_c2, m_h1;
     int rc;
     if ((rc = make_map(&m_cur, a.cur, a, C::SW, C::SROWS))) return rc;
     if ((rc = make_map(&m_prev, a.prev, a, C::TZ, C::TR))) return rc;
     if ((rc = make_map(&m_c1, a.c1, a, C::TZ, C::TR))) return rc;
     if ((rc = make_map(&m_c2, a.c2, a, C::TZ, C::TR))) return rc;
+    if ((rc = make_map(&m_h1, IMG == 2 ? a.h1 : a.c2, a, C::TZ, C::TR))) return rc;
     const int nchunks = (a.np + a.chunk - 1) / a.chunk;
     dim3 grid((a.nz + C::TZ - 1) / C::TZ, (a.nr + C::TR - 1) / C::TR, nchunks);
-    kern<<<grid, C::NTHREADS, C::SMEM, st>>>(a, m_cur, m_prev, m_c1, m_c2);
+    kern<<<grid, C::NTHREADS, C::SMEM, st>>>(a, m_cur, m_prev, m_c1, m_c2, m_h1);
     B2_CUDA(cudaGetLastError());
     count_launch();
     return 0;
 }
 
-static const int g_tma = []() { const char *e = getenv("B2FWI_TMA"); return e ? atoi(e) : 1; }();
+// B2FWI_TMA: bit 0 forward sweep, bit 1 adjoint + imaging sweep (A/B against the register-staged kernels)
+static const int g_tma = []() { const char *e = getenv("B2FWI_TMA"); return e ? atoi(e) : 3; }();
 
 bool tma_step_supported(const Layout &L, const StepArgs &a, int img)
 {
-    if (!g_tma || L.ndim != 3 || img != 0 || L.halo != 0) return false;
+    if (L.ndim != 3 || !(img == 0 || img == 2) || L.halo != 0) return false;
+    if (!(g_tma & (img == 0 ? 1 : 2))) return false;
+    if (img == 2 && (!a.h1 || !a.grad || (((uintptr_t)a.h1 | (uintptr_t)a.grad) & 15))) return false;
     if (!(L.R == 2 || L.R == 4)) return false;       // space_order 4 and 8
     // TMA: 16-byte aligned base and strides (rows are pitched to 32 floats); float4 stores as in step_kernel
     const uintptr_t al = (uintptr_t)a.cur | (uintptr_t)a.prev | (uintptr_t)a.c1 | (uintptr_t)a.c2 | (uintptr_t)a.out;
@@ -342,12 +357,16 @@ bool tma_step_supported(const Layout &L, const StepArgs &a, int img)
 // grid tile of the TMA kernel (pick_chunk sizes the plane chunks for it)
 void tma_tile_shape(int *tz, int *tr) { *tz = 128; *tr = 16; }
 
-int launch_step_tma(const Layout &L, const StepArgs &a, cudaStream_t st)
+int launch_step_tma(const Layout &L, const StepArgs &a, int img, cudaStream_t st)
 {
     const bool extras = a.illum != nullptr || a.d2u != nullptr;
+    if (img == 2) {
+        if (extras) { set_error("imaging sweep with forward extras"); return B2FWI_EINVAL; }
+        return L.R == 2 ? launch_tma<2, 5, 2, false>(a, st) : launch_tma<4, 3, 2, false>(a, st);
+    }
     switch (L.R) {
-    case 2: return extras ? launch_tma<2, 5, true>(a, st) : launch_tma<2, 5, false>(a, st);
-    case 4: return extras ? launch_tma<4, 3, true>(a, st) : launch_tma<4, 3, false>(a, st);
+    case 2: return extras ? launch_tma<2, 5, 0, true>(a, st) : launch_tma<2, 5, 0, false>(a, st);
+    case 4: return extras ? launch_tma<4, 3, 0, true>(a, st) : launch_tma<4, 3, 0, false>(a, st);
     default: set_error("no TMA variant for stencil radius %d", L.R); return B2FWI_EUNSUPPORTED;
     }
 }

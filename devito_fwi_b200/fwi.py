@@ -124,6 +124,20 @@ def fix_source_illumination(geometry, g):
 _WORKSPACE = {}
 
 
+CHECKPOINT = None    # None: checkpoint when the saved history would not fit; True / False: force (tests)
+
+
+def _use_checkpoints(model, nt):
+    if CHECKPOINT is not None:
+        return bool(CHECKPOINT)
+    import torch
+    hist = float(nt) * model.grid.slice_elems * 4
+    key = ('u', model.grid._key(), nt)
+    if key in _WORKSPACE:            # the history buffer already exists
+        return False
+    return hist > 0.6 * torch.cuda.mem_get_info()[0]
+
+
 def _saved_wavefield(model, nt, space_order):
     """Re-used nt-slice history buffer: only slots 0 and 1 need zeroing (every other slot is
     overwritten by the forward sweep), instead of a fresh zero-filled TimeFunction per shot."""
@@ -177,8 +191,13 @@ def _fwi_obj_single_dev(geometry, obs, misfit_func, direct_wave, resample_dt, ca
     model = geometry.model
     solver = AcousticWaveSolver(model, geometry, space_order=model.space_order, profile=False)
     illum = Function(name='illum', grid=model.grid) if calc_grad else None
-    wfd = _saved_wavefield(model, geometry.nt, model.space_order) if calc_grad else None
-    pred, wfd = solver.forward(vp=model.vp, save=calc_grad, u=wfd, illum=illum)[0:2]
+    if calc_grad and _use_checkpoints(model, geometry.nt):
+        # 3-D: the history does not fit in HBM -> on-device checkpoints, recomputed by the gradient (checkpoint.py)
+        _WORKSPACE.clear()
+        pred, wfd = solver.forward(vp=model.vp, save='checkpoint', illum=illum)[0:2]
+    else:
+        wfd = _saved_wavefield(model, geometry.nt, model.space_order) if calc_grad else None
+        pred, wfd = solver.forward(vp=model.vp, save=calc_grad, u=wfd, illum=illum)[0:2]
 
     dw = direct_wave
     if resample_dt is None:

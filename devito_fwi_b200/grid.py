@@ -118,6 +118,23 @@ class DeviceBuffer(object):
         self._newer = 'host'
         return self._host
 
+    def host_ro(self):
+        """Host view for reading only: brought up to date, but not marked as modified (so the next
+        kernel call does not upload it again)."""
+        newer = self._newer
+        h = self.host()
+        if newer != 'host':
+            self._newer = None
+        return h
+
+    def reduce(self, op):
+        """max / min over the domain; on the device when the device copy is current."""
+        if self._dev is not None and self._newer != 'host':
+            t = self._interior(self._dev)
+            return float(t.max() if op == 'max' else t.min())
+        h = self.host_ro()
+        return float(np.max(h) if op == 'max' else np.min(h))
+
     def set_host(self, value):
         h = self.host()
         h[...] = value
@@ -226,7 +243,7 @@ class Constant(object):
 
 def _values(f):
     if isinstance(f, (Function, TimeFunction)):
-        return f.data
+        return f._buf.host_ro()
     if hasattr(f, 'data'):
         return np.asarray(f.data)
     return np.asarray(f)
@@ -241,9 +258,13 @@ def norm(f, order=2):
 
 def mmax(f):
     """devito.builtins.mmax"""
+    if isinstance(f, (Function, TimeFunction)):
+        return np.dtype(f.dtype).type(f._buf.reduce('max'))
     return np.max(_values(f))
 
 
 def mmin(f):
     """devito.builtins.mmin"""
+    if isinstance(f, (Function, TimeFunction)):
+        return np.dtype(f.dtype).type(f._buf.reduce('min'))
     return np.min(_values(f))

@@ -163,10 +163,22 @@ class AcousticWaveSolver(object):
 
     # ------------------------------------------------------------------ operators
     def forward(self, src=None, rec=None, u=None, vp=None, save=None, **kwargs):
-        """Forward modelling: returns (rec, u, summary)   [wavesolver.py:76-114]."""
+        """Forward modelling: returns (rec, u, summary)   [wavesolver.py:76-114].
+        Extension: ``save='checkpoint'`` keeps on-device checkpoints instead of the full history and
+        returns a CheckpointedWavefield as ``u`` (accepted by ``gradient``), see checkpoint.py."""
         lib = _lib.lib()
         src = src or self.geometry.src
         rec = rec or self.geometry.rec
+        if isinstance(save, str):
+            if save != 'checkpoint':
+                raise ValueError("save must be None, a bool or 'checkpoint'")
+            from .checkpoint import checkpointed_forward
+            dt = float(kwargs.pop('dt', self.dt))
+            illum = kwargs.pop('illum', None)
+            timer = _Timer(self._profile)
+            cw = checkpointed_forward(self, src, rec, vp or self.model.vp, dt, illum=illum, **kwargs)
+            summary = self._summary('Forward', timer.stop(), max(cw.time_M - cw.time_m + 1, 0), BYTES_FWD)
+            return rec, cw, summary
         u = u or TimeFunction(name='u', grid=self.model.grid,
                               save=self.geometry.nt if save else None,
                               time_order=2, space_order=self.space_order)
@@ -232,8 +244,10 @@ class AcousticWaveSolver(object):
         v = v or TimeFunction(name='v', grid=self.model.grid,
                               time_order=2, space_order=self.space_order)
         vp = vp or self.model.vp
+        from .checkpoint import checkpointed_gradient, CheckpointedWavefield
+        if isinstance(u, CheckpointedWavefield):
+            return checkpointed_gradient(self, rec, v, grad, vp, dt, checkpoints=u, **kwargs)
         if checkpointing:
-            from .checkpoint import checkpointed_gradient
             return checkpointed_gradient(self, rec, v, grad, vp, dt, **kwargs)
 
         if not u.save:

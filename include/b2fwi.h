@@ -100,7 +100,9 @@ int b2fwi_prepare_coeffs(const b2fwi_grid *g, const float *vp, const float *damp
  * u:     save == 0 -> 3 haloed slices, slot = time % 3;  save != 0 -> nt haloed slices (slot = time).
  *        Initial state is read from the caller's u (slots time_m-1, time_m); results are left in place.
  * src:   [nt][src_map->npoint] (may be NULL with npoint == 0);  rec: [nt][rec_map->npoint], rows time_m..time_M written.
- * illum: optional haloed slice, incremented by sum_t u[t]^2 over t = time_m .. time_M+1  (fwi.py:170).
+ * illum: optional haloed slice, incremented by sum_t u[t]^2 over t = time_m .. time_M, plus u[nt-1]^2 when
+ *   time_M == nt-2 (the call that produces the last slice adds it): consecutive time windows tile the sum of
+ *   fwi.py:170 exactly.
  * d2u_out: optional haloed slices; slice (t - d2u_t0), t = time_m..time_M, receives (u[t-1] - 2u[t] + u[t+1]) / dt^2.
  */
 int b2fwi_forward(const b2fwi_grid *g, const float *vp, const float *coef, float dt,

@@ -143,6 +143,16 @@ def test_forward_gradient_3d(so):
     assert np.array_equal(grad_c.data, grad.data)
     grad_c2, _ = solver.gradient(rec=residual, u=None, checkpointing=True)
     assert np.array_equal(grad_c2.data, grad.data)
+    # forward(save='checkpoint') records the same data / illumination and hands its checkpoints to gradient()
+    il_full = b.Function(name='il', grid=model.grid)
+    solver.forward(save=True, illum=il_full)
+    il_ck = b.Function(name='il', grid=model.grid)
+    d_ck, cw, _ = solver.forward(save='checkpoint', illum=il_ck, segment=5)
+    assert np.array_equal(d_ck.data, d.data)
+    assert np.array_equal(il_ck.data, il_full.data)
+    assert rel_l2(il_full.data, np.sum(u64 ** 2, axis=0)) <= TOL_GRAD
+    grad_c3, _ = solver.gradient(rec=residual, u=cw)
+    assert np.array_equal(grad_c3.data, grad.data)
 
 
 def test_circle_fwi_kat_on_gpu():
