@@ -1,6 +1,8 @@
 """Turn ncu exports into the small text summaries committed under profiles/.
   launches:  python scripts/ncu_summary.py launches gpurun_out/launches_bench.csv
   full:      python scripts/ncu_summary.py full gpurun_out/prof.ncu-rep
+  traffic:   python scripts/ncu_summary.py traffic gpurun_out/launches_3d.csv [points_per_launch]
+             (csv of --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum)
 """
 import collections
 import csv
@@ -67,5 +69,36 @@ def full(path):
         print("  warp-state samples: " + ", ".join("%s %.1f%%" % (h, v) for v, h in sorted(st, reverse=True)[:9]))
 
 
+def traffic(path, npts=None):
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    hdr = rows[0]
+    iid, iname, imet = hdr.index("ID"), hdr.index("Kernel Name"), hdr.index("Metric Name")
+    ival, iunit = hdr.index("Metric Value"), hdr.index("Metric Unit")
+    scale = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3,
+             "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = collections.OrderedDict()
+    for r in rows[1:]:
+        d = per.setdefault(r[iid], {"name": r[iname]})
+        d[r[imet]] = float(r[ival].replace(",", "")) * scale.get(r[iunit], 1.0)
+    agg = collections.OrderedDict()
+    for d in per.values():
+        a = agg.setdefault(d["name"].split("(")[0], [0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += d.get("gpu__time_duration.sum", 0.0)
+        a[2] += d.get("dram__bytes_read.sum", 0.0)
+        a[3] += d.get("dram__bytes_write.sum", 0.0)
+    print("%-78s %5s %10s %9s %9s %10s" % ("kernel", "n", "avg_us", "rd_GB", "wr_GB", "dram_GB/s"))
+    for name, (n, t, rd, wr) in agg.items():
+        line = "%-78s %5d %10.1f %9.3f %9.3f %10.0f" % (name[:78], n, t / n, rd / n / 1e9, wr / n / 1e9,
+                                                       (rd + wr) / (t * 1e-6) / 1e9 if t else 0.0)
+        if npts and n and (rd + wr) / n > 1e9:
+            line += "  %.1f B/pt moved" % ((rd + wr) / n / npts)
+        print(line)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    fn = {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]]
+    if sys.argv[1] == "traffic" and len(sys.argv) > 3:
+        fn(sys.argv[2], float(sys.argv[3]))
+    else:
+        fn(sys.argv[2])

@@ -17,7 +17,11 @@ if what == "2d":
 else:
     geom = configs.layered3d(n=512, space_order=8, rec_decimate=8)
     solver = b.AcousticWaveSolver(geom.model, geom, space_order=8)
-    u = b.TimeFunction(name='u', grid=geom.model.grid, time_order=2, space_order=8)
-    solver.forward(u=u, time_M=8)
+    # 8 time steps in 2 checkpoint segments: forward (4 plain + 4 with u.dt2 store), then adjoint+imaging (4),
+    # recompute (4), adjoint+imaging (4) -- every TMA kernel variant of the 3-D shot gradient
+    rec, cw, _ = solver.forward(save='checkpoint', time_M=8)
+    res = b.Receiver(name='res', grid=geom.model.grid, time_range=geom.time_axis, coordinates=geom.rec_positions)
+    res._sdata.adopt_dev(rec._sdata.dev().clone())
+    solver.gradient(rec=res, u=cw, time_M=8)
     torch.cuda.synchronize()
 print("done")
