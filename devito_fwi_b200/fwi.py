@@ -284,11 +284,13 @@ def _is_w1d(misfit_func):
             and getattr(misfit_func, 'trans_type', None) == 'linear')
 
 
-def _stack_dev(receivers, shots, cache_owner, tag, stream=None):
+def _stack_dev(receivers, shots, cache_owner, tag, stream=None, after=None):
     """[nshots, nt, nrec] device tensor of a list of Receivers; re-used while the SAME list object is
     passed again and no record's host view has been handed out since (``.data`` access = possibly new
     host data = upload again). With ``stream`` the uploads are issued on that (copy) stream from the
-    records' pinned host buffers, so they overlap the forward sweep."""
+    records' pinned host buffers, so they overlap the forward sweep; ``after``: event marking the last
+    device-side read of the previous contents (the copy stream waits for it instead of for everything
+    queued on the compute stream - the forward sweep has already been launched there)."""
     import torch
     cache = cache_owner.__dict__.setdefault('_dev_stacks', {})
     hit = cache.get(tag)
@@ -300,12 +302,16 @@ def _stack_dev(receivers, shots, cache_owner, tag, stream=None):
         t = hit[2]
     else:
         t = torch.empty((len(shots),) + sd0.shape, dtype=torch.float32, device='cuda')
+    on_dev = [receivers[i]._sdata._newer == 'dev' or receivers[i]._sdata._host is None for i in shots]
     if stream is not None:
-        stream.wait_stream(torch.cuda.current_stream())
+        if after is not None and not any(on_dev):
+            stream.wait_event(after)
+        else:       # device-resident records were produced on the compute stream: order the copies behind it
+            stream.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream()):
         for k, i in enumerate(shots):
             sd = receivers[i]._sdata
-            if sd._newer == 'dev' or sd._host is None:
+            if on_dev[k]:
                 t[k].copy_(sd.dev())                                   # record lives on the device
             else:
                 t[k].copy_(sd._host_t if sd._host_t is not None else torch.from_numpy(sd._host),
@@ -321,14 +327,20 @@ def _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_gr
     shots = survey.shots
     w1d = _is_w1d(misfit_func)
     l2 = _is_l2(misfit_func) or w1d          # misfits evaluated on the device
+    if l2 and getattr(survey, '_copy_stream', None) is None:
+        survey._copy_stream = torch.cuda.Stream()
+        survey._misfit_done = None
+        # first use: the stacks are allocated before the sweep is queued
+        _stack_dev(obs, shots, survey, 'obs', survey._copy_stream)
+        if direct_wave is not None:
+            _stack_dev(direct_wave, shots, survey, 'dw', survey._copy_stream)
+    syn = survey.forward(save=calc_grad, illum=calc_grad)       # queued first: the GPU starts right away
     if l2:
         # observed / direct-wave records go up on a copy stream while the forward sweep runs
-        if getattr(survey, '_copy_stream', None) is None:
-            survey._copy_stream = torch.cuda.Stream()
-        obs_d = _stack_dev(obs, shots, survey, 'obs', survey._copy_stream)
-        dw_d = _stack_dev(direct_wave, shots, survey, 'dw', survey._copy_stream) if direct_wave is not None else None
-    syn = survey.forward(save=calc_grad, illum=calc_grad)
-    if l2:
+        done = survey._misfit_done
+        obs_d = _stack_dev(obs, shots, survey, 'obs', survey._copy_stream, done)
+        dw_d = _stack_dev(direct_wave, shots, survey, 'dw', survey._copy_stream, done) \
+            if direct_wave is not None else None
         # on-device least squares (misfit/misfit.py:5-9) incl. direct-wave subtraction (fwi.py:146-150)
         torch.cuda.current_stream().wait_stream(survey._copy_stream)
         if getattr(survey, '_res', None) is None:
@@ -347,6 +359,8 @@ def _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_gr
         else:
             _lib.check(lib.b2fwi_l2_misfit(_ptr(syn), _ptr(obs_d), _ptr(dw_d), syn.numel(), _ptr(survey._res),
                                            _ptr(survey._fval), _ptr(survey._scratch), _stream()))
+        survey._misfit_done = torch.cuda.Event()
+        survey._misfit_done.record()
         residual = survey._res
         fval = survey._fval            # stays on the device until the all-reduce
         residuals = [LazyResidual(residual[k]) for k in range(len(shots))]
@@ -398,7 +412,9 @@ def fwi_obj_multi(geometry, obs, misfit_func, direct_wave=None, mask=None, preco
     fval = .0
     residuals = []
     shots = dist.local_shots(geometry.nsrc)
-    same_dt = all(np.isclose(geometry.dt, obs[i].time_range.step) for i in shots)
+    dt0 = float(geometry.dt)      # np.isclose semantics on plain floats (29 numpy calls cost 0.5 ms per evaluation)
+    same_dt = all(abs(dt0 - float(obs[i].time_range.step)) <= 1e-8 + 1e-5 * abs(float(obs[i].time_range.step))
+                  for i in shots)
     survey = _resident_survey(geometry, shots) if same_dt else None
     if survey is not None:
         fval, residuals = _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_grad, acc)
