@@ -211,7 +211,9 @@ def run_b200(args):
                 "shots_per_s": round(nshots_job / ms_step_e2e * 1e3, 1),
                 "h2d_bytes_per_step": int(len(my_shots) * 2 * nt * nrec * 4 + npts * 4),
                 "d2h_bytes_per_step": int((2 * 300 * 106 + 1) * 8),
-                "note": "fwi_loss() with host obs / direct-wave records (pinned) and host model; residual list "
+                "note": "fwi_loss() with host obs / direct-wave records (pinned) and host model, device copies "
+                        "invalidated before every step; the H2D runs on a copy stream underneath the forward "
+                        "sweep (queued first), so it is hidden when it takes less than the sweep; residual list "
                         "stays on the device until read (LazyResidual)"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),

@@ -109,17 +109,21 @@ def test_forward_initial_state_time_window_and_scalar_vp():
     assert rel_l2(rec_a.data, d64) <= TOL_TRACE
 
 
-@pytest.mark.parametrize("so", [4, 8, 16])
-def test_forward_gradient_3d(so):
+@pytest.mark.parametrize("so,shape", [(4, (34, 29, 38)), (8, (34, 29, 38)), (16, (34, 29, 38)),
+                                      (8, (33, 31, 37)), (4, (21, 40, 135))])
+def test_forward_gradient_3d(so, shape):
+    """so = 4 / 8 run the TMA-staged kernels, so = 16 the cp.async one; the odd shapes give partial float4
+    quads, a second (partial) z tile, partial row tiles and several plane chunks."""
     b = _b()
-    shape, nbl = (34, 29, 38), 9
+    nbl = 9
     vp = np.full(shape, 1.5, dtype=np.float32)
     vp[..., 14:] = 2.2
     vp[10:20, 8:18, 20:30] = 2.9
     model = b.Model(origin=(0., 0., 0.), spacing=(10., 10., 10.), shape=shape, space_order=so, vp=vp,
                     nbl=nbl, bcs="damp")
-    src = np.array([[163.3, 141.2, 23.7]])
-    rx, ry = np.meshgrid(np.linspace(12.5, 320.1, 9), np.linspace(8.2, 271.9, 7), indexing='ij')
+    ext = [10. * (n - 1) for n in shape]
+    src = np.array([[0.49 * ext[0], 0.51 * ext[1], 23.7]])
+    rx, ry = np.meshgrid(np.linspace(12.5, ext[0] - 9.9, 9), np.linspace(8.2, ext[1] - 8.1, 7), indexing='ij')
     rec = np.stack([rx.ravel(), ry.ravel(), np.full(rx.size, 41.3)], axis=1)
     geom = b.AcquisitionGeometry(model, rec, src, 0., 150., f0=0.02, src_type='Ricker')
     solver = b.AcousticWaveSolver(model, geom, space_order=so)
