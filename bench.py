@@ -243,6 +243,10 @@ def run_b200(args):
             out["extra"] = extra_3d()
         except Exception as e:          # the headline line must survive a failure of the secondary workload
             out["extra"] = {"error": repr(e)[:200]}
+        try:
+            out["extra_2d"] = extra_2d()
+        except Exception as e:
+            out["extra_2d"] = {"error": repr(e)[:200]}
     print(json.dumps(out), flush=True)
 
 
@@ -314,6 +318,55 @@ def run_reference(args):
                                       % (sample, cores)},
            "e2e": {"value": v, "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
+
+
+def extra_2d():
+    """The other named 2-D configurations (BASELINE.json configs[0], [1], [3]) through the public API, CUDA-event
+    timed after a warm-up evaluation: circle (so=6, 11 shots) and Marmousi2 (31 shots) objective + gradient with
+    the L2 misfit, marmousi_fm forward modelling of 21 shots. Secondary numbers; the headline is configs[2]."""
+    import torch
+    from devito_fwi_b200 import fwi, configs
+    out = {}
+
+    def ev_time(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def objective(name, g_true, g_init, dw_geom, mask):
+        model = g_init.model
+        obs = fwi.fm_multi(g_true)
+        dw = fwi.fm_multi(dw_geom) if dw_geom is not None else None
+        nbl = model.nbl
+        x0 = (1. / (model.vp.data[nbl:-nbl, nbl:-nbl].astype(np.float64) ** 2)).ravel()
+        ms = ev_time(lambda: fwi.fwi_loss(x0, g_init, obs, fwi.least_square, dw, mask, True, True))
+        work = 2.0 * np.prod(model.grid.shape) * (g_init.nt - 2) * g_init.nsrc
+        svs = fwi._resident_surveys(g_init, list(range(g_init.nsrc)))
+        out[name] = {"grid": list(model.grid.shape), "so": model.space_order, "nt": g_init.nt, "shots": g_init.nsrc,
+                     "ms_per_objective_gradient": round(ms, 3), "gpts_per_s": round(work / ms / 1e6, 1),
+                     "shots_per_s": round(g_init.nsrc / ms * 1e3, 1),
+                     "launch_groups_shots_x_cluster": [[sv.nshots, int(sv.plan.cluster)] for sv in svs] if svs else None}
+        fwi._SURVEYS.clear()
+
+    g_true, g_init = configs.circle()
+    objective("circle_fwi", g_true, g_init, None, None)
+    g_true, g_init, g_const, mask = configs.marmousi2()
+    objective("marmousi2_fwi_L2", g_true, g_init, g_const, mask)
+    g_true, g_init, g_const, _ = configs.marmousi(nsrc=21, tn=4500.)
+    ms = ev_time(lambda: [fwi.fm_multi(g) for g in (g_true, g_init, g_const)])
+    model = g_true.model
+    work = 3.0 * np.prod(model.grid.shape) * (g_true.nt - 2) * g_true.nsrc
+    out["marmousi_fm"] = {"grid": list(model.grid.shape), "so": model.space_order, "nt": g_true.nt, "shots": g_true.nsrc,
+                          "models": 3, "ms_all_shots_3_models": round(ms, 3), "gpts_per_s": round(work / ms / 1e6, 1)}
+    fwi._SURVEYS.clear()
+    torch.cuda.empty_cache()
+    return out
 
 
 def extra_3d():

@@ -90,16 +90,17 @@ def fm_single(geometry, save=False):
 def fm_multi(geometry, save=False):
     """Forward modelling of every shot of a survey: list of Receivers   [fwi.py:67-81].
     2-D surveys run as one batched launch of the SM-resident engine (all shots concurrently)."""
-    survey = _resident_survey(geometry, list(range(geometry.nsrc))) if not save else None
-    if survey is None:
+    surveys = _resident_surveys(geometry, list(range(geometry.nsrc))) if not save else None
+    if not surveys:
         return [fm_single(_shot_geometry(geometry, i), save)[0] for i in range(geometry.nsrc)]
-    rec = survey.forward(save=False).clone()
     shots = []
-    for k in range(geometry.nsrc):
-        r = Receiver(name='rec', grid=geometry.grid, time_range=geometry.time_axis,
-                     coordinates=geometry.rec_positions)
-        r._sdata.adopt_dev(rec[k])
-        shots.append(r)
+    for survey in surveys:
+        rec = survey.forward(save=False).clone()
+        for k in range(survey.nshots):
+            r = Receiver(name='rec', grid=geometry.grid, time_range=geometry.time_axis,
+                         coordinates=geometry.rec_positions)
+            r._sdata.adopt_dev(rec[k])
+            shots.append(r)
     return shots
 
 
@@ -231,25 +232,40 @@ _SURVEYS = {}
 ENGINE = 'auto'     # 'auto' | 'stream' (force the per-shot streaming engine; used by the parity tests)
 
 
-def _resident_survey(geometry, shots):
-    """Cached ResidentSurvey for (geometry, shots), or None when the SM-resident engine does not apply."""
-    from .resident import ResidentSurvey
+def _resident_surveys(geometry, shots):
+    """Cached list of ResidentSurvey objects covering ``shots`` in order (one launch group each, see
+    resident.partition_shots; a single group whenever all shots fit one wave of clusters), or None when the
+    SM-resident engine does not apply."""
+    from .resident import ResidentSurvey, partition_shots
     if ENGINE == 'stream' or not shots or not ResidentSurvey.supported(geometry):
         return None
     model = geometry.model
     key = (id(model), model.grid._key(), model.space_order, tuple(shots), float(geometry.dt), geometry.nt,
            geometry.src_positions.tobytes(), geometry.rec_positions.tobytes(), geometry.f0, geometry.src_type,
            id(geometry._filter))
-    sv = _SURVEYS.get(key)
-    if sv is None:
+    svs = _SURVEYS.get(key)
+    if svs is None:
         if len(_SURVEYS) >= 4:
             _SURVEYS.clear()
+        groups = partition_shots(model.grid, model.space_order, model.nbl, len(shots))
+        if not groups:
+            return None
         try:
-            sv = ResidentSurvey(geometry, shots)
+            svs, k0 = [], 0
+            for count, cluster in groups:
+                svs.append(ResidentSurvey(geometry, shots[k0:k0 + count],
+                                          min_cluster=cluster if len(groups) > 1 else 1))
+                k0 += count
         except ValueError:
             return None
-        _SURVEYS[key] = sv
-    return sv
+        _SURVEYS[key] = svs
+    return svs
+
+
+def _resident_survey(geometry, shots):
+    """The survey of ``shots`` when they form a single launch group (the common case), else None."""
+    svs = _resident_surveys(geometry, shots)
+    return svs[0] if svs and len(svs) == 1 else None
 
 
 class LazyResidual(object):
@@ -415,9 +431,12 @@ def fwi_obj_multi(geometry, obs, misfit_func, direct_wave=None, mask=None, preco
     dt0 = float(geometry.dt)      # np.isclose semantics on plain floats (29 numpy calls cost 0.5 ms per evaluation)
     same_dt = all(abs(dt0 - float(obs[i].time_range.step)) <= 1e-8 + 1e-5 * abs(float(obs[i].time_range.step))
                   for i in shots)
-    survey = _resident_survey(geometry, shots) if same_dt else None
-    if survey is not None:
-        fval, residuals = _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_grad, acc)
+    surveys = _resident_surveys(geometry, shots) if same_dt else None
+    if surveys:
+        for survey in surveys:
+            fval_, res_ = _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_grad, acc)
+            fval = fval_ + fval          # device tensor (on-device misfits) or float
+            residuals += res_
     else:
         for i in shots:
             geom_i = _shot_geometry(geometry, i)

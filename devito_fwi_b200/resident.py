@@ -68,6 +68,47 @@ def choose_plan(grid, space_order, nbl, nshots):
     return best
 
 
+def partition_shots(grid, space_order, nbl, nshots):
+    """Split ``nshots`` concurrent shots into launch groups [(count, min_cluster), ...].
+
+    One launch keeps ``slots`` clusters resident; more shots than that run in waves, and the last wave is
+    usually far from full. Cheaper: give each wave its own launch and its own decomposition - a full wave of
+    the smallest cluster, then the remainder on wider clusters (fewer rows per CTA = faster steps). The cost of
+    a group is one wave = rows per CTA (x a mild penalty for wider barriers) + a fixed part (per-step barrier and
+    dependency latency do not shrink with the strip: measured on Marmousi2, 70 -> 53 rows per CTA takes a wave
+    from 20 to 17.5 ms, i.e. the fixed part is worth ~60 rows); best(n) = min over plans p of cost_p if
+    n <= slots_p else cost_p + best(n - slots_p)."""
+    g = grid_struct(grid, space_order)
+    cands, seen = [], set()
+    for cmin in range(1, 9):
+        plan = plan_model(grid, space_order, nbl, cmin)
+        if plan is None or plan.cluster in seen:
+            continue
+        seen.add(plan.cluster)
+        n = ctypes.c_int32()
+        rc = _lib.lib().b2fwi_res2d_max_active_clusters(ctypes.byref(g), ctypes.byref(plan), ctypes.byref(n))
+        if rc != 0 or n.value <= 0:
+            continue
+        cands.append((plan.rows_cta * (1.0 + 0.02 * plan.cluster) + 60.0, int(n.value), int(plan.cluster)))
+    if not cands:
+        return None
+    memo = {}
+
+    def best(n):
+        if n <= 0:
+            return 0.0, []
+        if n not in memo:
+            opts = []
+            for cost, slots, cluster in cands:
+                k = min(n, slots)
+                rest_cost, rest = best(n - k)
+                opts.append((cost + rest_cost, [(k, cluster)] + rest))
+            memo[n] = min(opts, key=lambda o: o[0])
+        return memo[n]
+
+    return best(int(nshots))[1]
+
+
 def build_maps(grid, plan, R, inj_coords, itp_coords=None):
     """numpy arrays of struct b2fwi_res2d_maps for a list of shots.
 

@@ -117,6 +117,34 @@ def test_objective_resident_vs_streaming_vs_oracle():
     assert np.isclose(f2, f_r, rtol=1e-9) and not g2.any()
 
 
+def test_objective_in_launch_groups_matches_single_group(monkeypatch):
+    """Surveys with more shots than one wave of clusters are split into launch groups with their own cluster
+    size (resident.partition_shots). A forced split (3 shots on 4-CTA clusters + 2 shots on 6-CTA clusters)
+    must give the objective, gradient, residuals and fm_multi records of the single-group run."""
+    from devito_fwi_b200 import configs, fwi, resident
+    g_true, g_init, g_const, mask = configs.marmousi(nsrc=5)
+    x = (1. / (g_init.model.vp.data[40:-40, 40:-40].astype(np.float64) ** 2)).ravel()
+    groups = resident.partition_shots(g_init.model.grid, 8, 40, 5)
+    assert groups == [(5, groups[0][1])]                      # five shots: one wave, one group
+    assert sum(k for k, _ in resident.partition_shots(g_init.model.grid, 8, 40, 300)) == 300
+    obs, dw = fwi.fm_multi(g_true), fwi.fm_multi(g_const)
+    f1, g1, r1 = fwi.fwi_loss(x, g_init, obs, fwi.least_square, dw, mask, True, True)
+    r1 = [np.asarray(r).copy() for r in r1]
+    fwi._SURVEYS.clear()
+    monkeypatch.setattr(resident, 'partition_shots', lambda *a, **k: [(3, 4), (2, 6)])
+    svs = fwi._resident_surveys(g_init, list(range(5)))
+    assert [sv.nshots for sv in svs] == [3, 2] and [sv.plan.cluster for sv in svs] == [4, 6]
+    assert [sv.shots for sv in svs] == [[0, 1, 2], [3, 4]]
+    f2, g2, r2 = fwi.fwi_loss(x, g_init, obs, fwi.least_square, dw, mask, True, True)
+    obs2 = fwi.fm_multi(g_true)
+    fwi._SURVEYS.clear()
+    assert abs(f2 - f1) <= 1e-6 * abs(f1) and rel_l2(g2, g1) < 1e-5
+    assert len(r2) == 5
+    for k in range(5):
+        assert rel_l2(np.asarray(r2[k]), r1[k]) < 1e-5
+        assert rel_l2(obs2[k].data, obs[k].data) < 1e-5
+
+
 def test_resident_many_shots_small_grid_vs_streaming():
     """More shots than resident clusters (several waves), a 2-CTA cluster, sources / receivers in the
     sponge and outside the grid: the batched resident engine must agree with the per-shot streaming
