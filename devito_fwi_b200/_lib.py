@@ -100,6 +100,7 @@ PROTOTYPES = {
     "b2fwi_forward": (ctypes.c_int, [_G, _P, _P, _F, _I, _I, _I, _P, _S, _P, _S, _P, _I, _P, _P, _I, _P]),
     "b2fwi_gradient": (ctypes.c_int, [_G, _P, _P, _F, _I, _I, _I, _P, _S, _P, _I, _I, _P, _P, _P]),
     "b2fwi_adjoint": (ctypes.c_int, [_G, _P, _P, _F, _I, _I, _I, _P, _S, _P, _S, _P, _P]),
+    "b2fwi_born": (ctypes.c_int, [_G, _P, _P, _F, _I, _I, _I, _P, _S, _P, _S, _P, _P, _P, _P, _P]),
     "b2fwi_geometry_mask": (ctypes.c_int, [_G, _I, _P, _I, _P, _P]),
     "b2fwi_crop_mask_accumulate": (ctypes.c_int, [_G, _I, _P, _P, _P, _P]),
     "b2fwi_res2d_plan_model": (ctypes.c_int, [_G, _I, _I, _P]),

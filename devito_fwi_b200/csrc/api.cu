@@ -248,6 +248,47 @@ int b2fwi_adjoint(const b2fwi_grid *g, const float *vp, const float *coef, float
                     stream);
 }
 
+int b2fwi_born(const b2fwi_grid *g, const float *vp, const float *coef, float dt,
+               int32_t nt, int32_t time_m, int32_t time_M,
+               const float *src, const b2fwi_sparse *src_map,
+               float *rec, const b2fwi_sparse *rec_map,
+               const float *dm, float *u, float *U, float *scratch, void *stream)
+{
+    Layout L;
+    int rc = make_layout(g, &L);
+    if (rc) return rc;
+    if ((rc = check_time(nt, time_m, time_M))) return rc;
+    B2_CHECK_ARG(vp && coef && u && U && dm && scratch, "NULL field pointer");
+    const int nsrc = src_map ? src_map->npoint : 0, nrec = rec_map ? rec_map->npoint : 0;
+    B2_CHECK_ARG(nsrc == 0 || src, "src is NULL with %d source points", nsrc);
+    B2_CHECK_ARG(nrec == 0 || rec, "rec is NULL with %d receiver points", nrec);
+    cudaStream_t st = (cudaStream_t)stream;
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_stencil_weights(L, &a);
+    a.c1 = coef; a.c2 = coef + L.elems;
+    a.box = reinterpret_cast<const int *>(coef + 2 * L.elems);
+    a.inv_dt2 = 1.f / (dt * dt);
+    a.chunk = pick_chunk(L);
+    for (int time = time_m; time <= time_M; time++) {
+        const int64_t sn = (time + 1) % 3, sc = time % 3, sp = (time - 1) % 3;
+        // background wavefield, u.dt2[time] into the scratch slice (the injection kernel patches it at the source cells)
+        a.out = u + sn * L.elems; a.cur = u + sc * L.elems; a.prev = u + sp * L.elems;
+        a.d2u = scratch;
+        if ((rc = launch_step(L, a, 0, st))) return rc;
+        if (nsrc > 0 && (rc = launch_inject(u + sn * L.elems, vp, dt, src + (int64_t)time * nsrc, src_map, scratch,
+                                            a.cur, a.prev, a.inv_dt2, st)))
+            return rc;
+        // scattered wavefield
+        a.out = U + sn * L.elems; a.cur = U + sc * L.elems; a.prev = U + sp * L.elems;
+        a.d2u = nullptr;
+        if ((rc = launch_step(L, a, 0, st))) return rc;
+        if ((rc = launch_born_source(L, U + sn * L.elems, a.c2, dm, scratch, st))) return rc;
+        if (nrec > 0 && (rc = launch_interp(U + sc * L.elems, rec + (int64_t)time * nrec, rec_map, st))) return rc;
+    }
+    return 0;
+}
+
 int b2fwi_geometry_mask(const b2fwi_grid *g, int32_t nbl, const double *pts, int32_t npts, double *mask_out,
                         void *stream)
 {

@@ -559,6 +559,23 @@ int launch_coeffs(const Layout &L, const float *vp, const float *damp, float dt,
     return 0;
 }
 
+// Born source term: field -= (c2 * dm) * d2u   (q = -dm * u.dt2 entering U.forward with the factor c2)
+__global__ void born_source_kernel(float *__restrict__ field, const float *__restrict__ c2,
+                                   const float *__restrict__ dm, const float *__restrict__ d2u, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) field[i] = __fmaf_rn(-__fmul_rn(c2[i], dm[i]), d2u[i], field[i]);
+}
+
+int launch_born_source(const Layout &L, float *field, const float *c2, const float *dm, const float *d2u,
+                       cudaStream_t st)
+{
+    born_source_kernel<<<(unsigned)((L.elems + 255) / 256), 256, 0, st>>>(field, c2, dm, d2u, L.elems);
+    B2_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
 __global__ void accum_sq_kernel(float *__restrict__ acc, const float *__restrict__ f, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

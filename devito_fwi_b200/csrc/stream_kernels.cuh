@@ -36,6 +36,8 @@ int launch_inject(float *field, const float *vp, float dt, const float *vals, co
 int launch_interp(const float *field, float *out, const b2fwi_sparse *m, cudaStream_t st);
 int launch_coeffs(const Layout &L, const float *vp, const float *damp, float dt, float *coef, cudaStream_t st);
 int launch_accum_sq(const Layout &L, float *acc, const float *f, cudaStream_t st);
+int launch_born_source(const Layout &L, float *field, const float *c2, const float *dm, const float *d2u,
+                       cudaStream_t st);
 int launch_geometry_mask(const b2fwi_grid *g, int nbl, const double *pts, int npts, double *mask, cudaStream_t st);
 int launch_crop_mask_acc(const b2fwi_grid *g, const Layout &L, int nbl, const float *field, const double *mask,
                          double *out, cudaStream_t st);

@@ -271,8 +271,45 @@ class AcousticWaveSolver(object):
         return grad, summary
 
     def jacobian(self, dmin, src=None, rec=None, u=None, U=None, vp=None, **kwargs):
-        raise NotImplementedError("the linearised Born operator is outside the FWI-gradient hot path "
-                                  "(SURVEY.md section 8f, row 4)")
+        """Linearised (Born) modelling: returns (rec, u, U, summary)   [wavesolver.py:207-242].
+        ``dmin``: perturbation of the squared slowness, a Function or an array of the padded grid shape."""
+        import torch
+        lib = _lib.lib()
+        src = src or self.geometry.src
+        rec = rec or self.geometry.rec
+        u = u or TimeFunction(name='u', grid=self.model.grid, time_order=2, space_order=self.space_order)
+        U = U or TimeFunction(name='U', grid=self.model.grid, time_order=2, space_order=self.space_order)
+        if u.save or U.save:
+            raise ValueError("the Born operator runs on ring-buffer wavefields (save=None), as in the reference")
+        vp = vp or self.model.vp
+        dt = float(kwargs.pop('dt', self.dt))
+        nt = min(src.nt, rec.nt)
+        time_m, time_M = self._time_bounds(kwargs, nt)
+        grid = self.model.grid
+        if isinstance(dmin, Function):
+            dm = dmin
+        else:
+            dm = Function(name='dm', grid=grid, space_order=0)
+            arr = np.asarray(dmin, dtype=np.float32)
+            if arr.shape != grid.shape:
+                raise ValueError("dm must have the padded grid shape %s (got %s)" % (grid.shape, arr.shape))
+            dm.data[...] = arr
+        vp_dev = self._vp_dev(vp)
+        coef = self._coeffs(vp_dev, dt)
+        src_map = sparse_map(grid, src.coordinates.data)
+        rec_map = sparse_map(grid, rec.coordinates.data)
+        src_dev = src._sdata.dev()
+        rec_dev = rec._sdata.dev(write=True)
+        u_dev, U_dev = self._field_dev(u, write=True), self._field_dev(U, write=True)
+        scratch = torch.empty(grid.slice_shape, dtype=torch.float32, device='cuda')
+        g = self._gs()
+        timer = _Timer(self._profile)
+        _lib.check(lib.b2fwi_born(
+            ctypes.byref(g), _ptr(vp_dev), _ptr(coef), ctypes.c_float(dt), nt, time_m, time_M,
+            _ptr(src_dev), src_map.byref(), _ptr(rec_dev), rec_map.byref(),
+            _ptr(dm._buf.dev()), _ptr(u_dev), _ptr(U_dev), _ptr(scratch), _stream()))
+        summary = self._summary('Born', timer.stop(), max(time_M - time_m + 1, 0), 2 * BYTES_FWD + 16)
+        return rec, u, U, summary
 
     # Backward compatibility
     born = jacobian

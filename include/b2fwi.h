@@ -135,6 +135,22 @@ int b2fwi_adjoint(const b2fwi_grid *g, const float *vp, const float *coef, float
                   float *v, void *stream);
 
 /*
+ * Linearised (Born) forward operator (operators.py:228-273 BornOperator; AcousticWaveSolver.jacobian / .born,
+ * wavesolver.py:207-242). Per time step, in the reference's expression order:
+ *   u[time+1] = step(u[time], u[time-1]);  u[time+1] += inject(src[time]);
+ *   U[time+1] = step(U[time], U[time-1]) - c2 * dm * u.dt2[time],   u.dt2 = (u[time-1] - 2u[time] + u[time+1]) / dt^2
+ *   rec[time] = interpolate(U[time])
+ * (c2 = dt^2 / (m + dt*damp): the source term q = -dm * u.dt2 of iso_stencil solved for U.forward.)
+ * dm: haloed slice, perturbation of the squared slowness.  u, U: 3 haloed slices each (ring, in/out).
+ * scratch: one haloed slice of workspace (u.dt2 of the current step).
+ */
+int b2fwi_born(const b2fwi_grid *g, const float *vp, const float *coef, float dt,
+               int32_t nt, int32_t time_m, int32_t time_M,
+               const float *src, const b2fwi_sparse *src_map,
+               float *rec, const b2fwi_sparse *rec_map,
+               const float *dm, float *u, float *U, float *scratch, void *stream);
+
+/*
  * Per-shot host post-processing of fwi.py:104-129,166-171 moved on device (2-D models):
  *   mask[i,j] = prod_k (1 - exp(-.5*((z_j - c_k0)^2 + (x_i - c_k1)^2) / sigma^2)),  sigma = dx + dz,
  * over the source and all receivers, axes swapped exactly as fix_source_illumination does

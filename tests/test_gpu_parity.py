@@ -264,3 +264,56 @@ def test_fwi_obj_multi_vs_oracle():
     # forward-only evaluation (line search, minimize.py:67-68)
     f2, g2, _ = b.fwi.fwi_obj_multi(g_init, obs, b.fwi.least_square, None, mask, True, False)
     assert np.isclose(f2, f, rtol=1e-6) and not g2.any()
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_born_adjoint_and_linearisation(ndim):
+    """The linearised forward operator (solver.jacobian / .born, wavesolver.py:207-242) against the two
+    properties Devito's own test-suite checks for it: <J dm, d> == <dm, J^T d> with J^T = solver.gradient
+    (itself pinned to the oracle above), and F(m + eps dm) - F(m) -> eps J dm."""
+    b = _b()
+    so, nbl = 8, 12
+    shape = (61, 53) if ndim == 2 else (30, 27, 33)
+    vp = np.full(shape, 1.6, dtype=np.float32)
+    vp[..., shape[-1] // 2:] = 2.3
+    model = b.Model(origin=(0.,) * ndim, spacing=(10.,) * ndim, shape=shape, space_order=so, vp=vp, nbl=nbl,
+                    bcs="damp")
+    ext = [10. * (n - 1) for n in shape]
+    src = np.array([[0.5 * e for e in ext[:-1]] + [20.]])
+    nrec = 23
+    rec = np.zeros((nrec, ndim))
+    rec[:, 0] = np.linspace(5., ext[0] - 5., nrec)
+    if ndim == 3:
+        rec[:, 1] = np.linspace(ext[1] - 7., 9., nrec)
+    rec[:, -1] = 30.
+    geom = b.AcquisitionGeometry(model, rec, src, 0., 260., f0=0.025, src_type='Ricker')
+    solver = b.AcousticWaveSolver(model, geom, space_order=so)
+    rng = np.random.default_rng(3)
+    dm = np.zeros(model.grid.shape, dtype=np.float32)
+    inner = tuple(slice(nbl + 6, n - nbl - 6) for n in model.grid.shape)
+    from scipy.ndimage import gaussian_filter
+    dm[inner] = gaussian_filter(rng.standard_normal(dm[inner].shape), 2.0).astype(np.float32) * 0.05
+
+    d0, u, _ = solver.forward(save=True)
+    du, u_b, U, _ = solver.jacobian(dm)
+    assert np.isfinite(du.data).all() and np.abs(du.data).max() > 0
+    # the background wavefield of the Born operator is the forward wavefield
+    assert np.array_equal(u_b.data[(geom.nt - 1) % 3], u.data[geom.nt - 1])
+    # adjoint test (fp32: Devito's test_adjoint_J uses 1e-5 in fp32 as well... we allow 5e-5)
+    grad, _ = solver.gradient(rec=du, u=u)
+    term1 = float(np.dot(np.float64(grad.data).ravel(), np.float64(dm).ravel()))
+    term2 = float(np.sum(np.float64(du.data) ** 2))
+    print("%d-D Born adjoint test: <J^T du, dm> = %.8e, |du|^2 = %.8e, rel %.2e" % (ndim, term1, term2,
+                                                                                 abs(term1 - term2) / term2))
+    assert abs(term1 - term2) <= 5e-5 * term2
+    # linearisation: m = 1/vp^2 on the padded grid
+    m0 = 1.0 / np.float64(model.vp.data) ** 2
+    errs = []
+    for eps in (0.5, 0.25):
+        vp_eps = b.Function(name='vpe', grid=model.grid)
+        vp_eps.data[...] = np.float32(1.0 / np.sqrt(m0 + eps * np.float64(dm)))
+        d_eps, _, _ = solver.forward(vp=vp_eps)
+        lin = np.float64(d_eps.data) - np.float64(d0.data) - eps * np.float64(du.data)
+        errs.append(np.linalg.norm(lin) / np.linalg.norm(eps * np.float64(du.data)))
+    print("   linearisation error at eps=0.5, 0.25: %.3e %.3e" % tuple(errs))
+    assert errs[1] < 0.6 * errs[0] and errs[1] < 0.1          # first-order remainder: halves with eps
