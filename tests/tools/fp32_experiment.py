@@ -1,7 +1,7 @@
 """Emulate the kernel's fp32 arithmetic variants in numpy and measure the distance to the fp64 oracle
 (one Marmousi shot)."""
 import sys, os
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import ref
 import devito_fwi_b200 as b
