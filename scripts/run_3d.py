@@ -17,13 +17,17 @@ model = geom.model
 npts = int(np.prod(model.grid.shape))
 solver = b.AcousticWaveSolver(model, geom, space_order=so)
 t0 = time.time()
-rec, cw, s_f = solver.forward(save='checkpoint')     # forward modelling + on-device checkpoints (pass 1)
-# residual = the data themselves (any record works for timing; parity is tested at small sizes)
 res = b.Receiver(name='res', grid=model.grid, time_range=geom.time_axis, coordinates=geom.rec_positions)
-res._sdata.adopt_dev(rec._sdata.dev().clone())
-torch.cuda.synchronize()
-grad, s_g = solver.gradient(rec=res, u=cw)           # pass 2: recompute (+u.dt2 store) + adjoint/imaging
-torch.cuda.synchronize()
+for rep in range(2):   # shot 1 pays the one-off allocations (tens of GB of checkpoints), shot 2 is the steady state of a survey
+    rec, cw, s_f = solver.forward(save='checkpoint')     # forward modelling + on-device checkpoints (pass 1)
+    # residual = the data themselves (any record works for timing; parity is tested at small sizes)
+    res._sdata.adopt_dev(rec._sdata.dev().clone())
+    torch.cuda.synchronize()
+    grad, s_g = solver.gradient(rec=res, u=cw)           # pass 2: recompute (+u.dt2 store) + adjoint/imaging
+    torch.cuda.synchronize()
+    if rep == 0:
+        first = round(s_f.time + s_g.time, 3)
+        del cw, grad
 steps = geom.nt - 2
 gmax = float(grad._buf.dev().abs().max())
 out = {"workload": "layered3d %d^3 (+2*%d) so=%d nt=%d, %d receivers" % (n, model.nbl, so, geom.nt, geom.nrec),
@@ -32,7 +36,7 @@ out = {"workload": "layered3d %d^3 (+2*%d) so=%d nt=%d, %d receivers" % (n, mode
        "gradient_checkpointed": {"s": round(s_g.time, 4),
                                  "sweeps": "recompute(+u.dt2 store) + adjoint/imaging",
                                  "gpts_per_s_2sweeps": round(2 * npts * steps / s_g.time / 1e9, 1)},
-       "shot_gradient_s": round(s_f.time + s_g.time, 3),
+       "shot_gradient_s": round(s_f.time + s_g.time, 3), "first_shot_gradient_s_incl_allocations": first,
        "shot_gradient": {"sweeps": "forward(+checkpoints) + recompute(+u.dt2 store) + adjoint/imaging",
                          "GBs_alg_52B": round(52.0 * npts * steps / (s_f.time + s_g.time) / 1e9, 1),
                          "frac_hbm_52B": round(52.0 * npts * steps / (s_f.time + s_g.time) / 1e9 / peak, 3),
