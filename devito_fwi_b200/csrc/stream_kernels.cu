@@ -381,13 +381,16 @@ int pick_chunk(const Layout &L)
     if (L.ndim != 3) return 1;
     int tzc, trc, bps;
     tile_shape(L.ndim, &tzc, &trc, &bps);
-    static int n_slots = 0;
-    if (n_slots == 0) {
-        int dev = 0, sms = 148;
+    if (L.halo == 0 && tma_enabled(0)) { tma_tile_shape(L.R, &tzc, &trc); bps = 1; }     // one TMA CTA per SM
+    else if (L.R > 4) { tzc = 64; trc = 16; bps = 2; }
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess)
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        n_slots = bps * sms;
     }
+    const int n_slots = bps * sms;
     const long tiles = (long)((L.nz + tzc - 1) / tzc) * ((L.nr + trc - 1) / trc);
     int best_nc = 1;
     double best_cost = 1e30;

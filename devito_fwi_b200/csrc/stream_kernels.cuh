@@ -31,6 +31,8 @@ int launch_step(const Layout &L, StepArgs a, int img, cudaStream_t st);
 // TMA-staged 3-D sweeps: forward, adjoint + imaging from u.dt2 (stream_tma.cu)
 bool tma_step_supported(const Layout &L, const StepArgs &a, int img);
 int launch_step_tma(const Layout &L, const StepArgs &a, int img, cudaStream_t st);
+void tma_tile_shape(int R, int *tz, int *tr);
+bool tma_enabled(int img);
 int launch_inject(float *field, const float *vp, float dt, const float *vals, const b2fwi_sparse *m,
                   float *d2u, const float *cur, const float *prev, float inv_dt2, cudaStream_t st);
 int launch_interp(const float *field, float *out, const b2fwi_sparse *m, cudaStream_t st);

@@ -71,21 +71,28 @@ static __device__ __forceinline__ float4 lds4(uint32_t addr)
 
 template <int R, int NPCC, int IMG>
 struct TmaCfg {
-    static constexpr int TZQ = 32, TR = 16, TZ = 4 * TZQ, ZH = 4, SW = TZ + 2 * ZH, SROWS = TR + 2 * R;
+    // so <= 8: 128 z x 16 rows, 16 compute warps. so > 8: the 2R+1 float4 register pipeline needs > 96 registers per
+    // thread, so the tile is 64 z x 16 rows with 8 compute warps (register cap 224) and a 17-plane ring of
+    // correspondingly smaller boxes still fits 227 KB.
+    static constexpr int TZQ = (R <= 4) ? 32 : 16, TR = 16, TZ = 4 * TZQ, ZH = 4 * ((R + 3) / 4);
+    static constexpr int SW = TZ + 2 * ZH, SROWS = TR + 2 * R;
     static constexpr int NQ = 2 * R + 1, NCUR = NQ;
-    static constexpr int CUR_BYTES = SROWS * SW * 4;       // one u[t] box
-    static constexpr int PL_BYTES = TR * TZ * 4;           // one pointwise-operand box
-    static constexpr int NARR = (IMG == 2) ? 4 : 3;        // prev, c2, c1 [, u.dt2]
+    static constexpr int CUR_BYTES = SROWS * SW * 4;                       // one u[t] box
+    static constexpr int CUR_STRIDE = (CUR_BYTES + 127) / 128 * 128;       // ring stage stride (TMA destinations: 128 B)
+    static constexpr int PL_BYTES = TR * TZ * 4;                           // one pointwise-operand box
+    static constexpr int NARR = (IMG == 2) ? 4 : 3;                        // prev, c2, c1 [, u.dt2]
     static constexpr int PCC_BYTES = NARR * PL_BYTES;
+    // operand-ring stage of unroll slot j is the compile-time j % NPCC when the ring turns a whole, odd number of
+    // times per group of NQ planes; otherwise stage and parity are carried in two registers
+    static constexpr bool PCT = (NQ % NPCC == 0) && (((NQ / NPCC) & 1) == 1);
     static constexpr int NCONS = TZQ * TR, NTHREADS = NCONS + 32;
-    static constexpr int BAR_OFF = NCUR * CUR_BYTES + NPCC * PCC_BYTES;     // mbarriers (64 slots reserved)
+    static constexpr int BAR_OFF = NCUR * CUR_STRIDE + NPCC * PCC_BYTES;    // mbarriers (64 slots reserved)
     static constexpr int W_OFF = BAR_OFF + 64 * 8;                          // Laplacian weights, 32 floats
     static constexpr int TH_OFF = W_OFF + 32 * 4;                           // per-thread constants, uint4 each
     static constexpr int SMEM = TH_OFF + NCONS * 16;
-    static_assert(R <= 4, "z halo of one float4");
-    static_assert(NQ % NPCC == 0, "stage indices must be compile-time under the NQ-fold unroll");
-    static_assert(CUR_BYTES % 128 == 0 && PL_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
-    static_assert(2 * NCUR + NPCC <= 64, "barrier slots");
+    static_assert(R >= 1 && R <= 8, "stencil radius");
+    static_assert(PL_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
+    static_assert(2 * NCUR + NPCC <= 64 && 2 + 3 * R <= 32, "barrier / weight slots");
 };
 
 // IMG: 0 forward sweep (EXTRAS: illumination / u.dt2 store), 2 adjoint sweep + imaging from stored u.dt2.
@@ -100,7 +107,7 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(smem);
     // layout: u[t] ring [NCUR][SROWS][SW] | operand ring [NPCC][3][TR][TZ] | mbarriers | weights | per-thread consts
-    const uint32_t pcc_s = smem_s + NCUR * C::CUR_BYTES;
+    const uint32_t pcc_s = smem_s + NCUR * C::CUR_STRIDE;
     const uint32_t full_c = smem_s + C::BAR_OFF;                          // [NCUR]
     const uint32_t empty = full_c + NCUR * 8;                             // [NCUR]
     const uint32_t full_p = empty + NCUR * 8;                             // [NPCC]
@@ -135,7 +142,7 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
         // Loop-invariant per-thread values take a round trip through shared memory: read back with a volatile
         // load they stay in registers, whereas ptxas re-derives them from %tid / the constant bank in every
         // plane otherwise (the sweep is issue-sensitive).
-        const int tz = tid & 31, tr = tid >> 5;
+        const int tz = tid % C::TZQ, tr = tid / C::TZQ;
         uint4 c;
         c.x = smem_s + (uint32_t)((R + tr) * SW + ZH + 4 * tz) * 4u;       // this thread's float4 in u[t] stage 0
         c.y = pcc_s + (uint32_t)tid * 16u;                                 // ... in operand stage 0, array 0
@@ -151,7 +158,7 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
             auto issue_cur = [&](int k) {
                 const uint32_t bar = full_c + 8 * (k % NCUR);
                 mbar_expect_tx(bar, C::CUR_BYTES);
-                tma_load_3d(smem_s + (k % NCUR) * C::CUR_BYTES, &m_cur, bar, ztile0 - ZH, r0 - R, p_begin + k);
+                tma_load_3d(smem_s + (k % NCUR) * C::CUR_STRIDE, &m_cur, bar, ztile0 - ZH, r0 - R, p_begin + k);
             };
             auto issue_pcc = [&](int k) {
                 const int p = p_begin + k;
@@ -198,9 +205,9 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
         }
     }
     const uint32_t bar_fc = bars, bar_em = bars + NCUR * 8, bar_fp = bars + 2 * NCUR * 8;
-    const int tz = tid & 31, tr = tid >> 5;
+    const int tz = tid % C::TZQ, tr = tid / C::TZQ;
     const bool active = (r0 + tr < a.nr) && (ztile0 + tz * 4 < a.nz);
-    const bool lane0 = tz == 0;
+    const bool lane0 = (tid & 31) == 0;
     const uint32_t sp4 = (uint32_t)(a.sp >> 2);
     const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
 #define F4(ptr) reinterpret_cast<const float4 *>(ptr)
@@ -217,13 +224,14 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
     for (int i = 0; i < R; i++) {
         if (i < ncur) {
             mbar_wait(bar_fc + 8 * i, 0);
-            q[R + i] = lds4(ctr_s + i * C::CUR_BYTES);
+            q[R + i] = lds4(ctr_s + i * C::CUR_STRIDE);
         } else {
             q[R + i] = zero4();
         }
     }
 
     uint32_t idx = own4 + (uint32_t)p_begin * sp4;
+    uint32_t ps = 0, pp = 0;         // operand-ring stage / parity when they are not compile-time (see TmaCfg::PCT)
     // one group = NQ planes. EDGE = false: the whole group and its feed planes exist, no per-plane range tests.
     auto group = [&](auto edge_tag, int pb, uint32_t par) {
         constexpr bool EDGE = decltype(edge_tag)::value;
@@ -239,21 +247,28 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
                 const int sf = (j + R) % NQ;
                 if (!EDGE || i + R < ncur) {
                     mbar_wait(bar_fc + 8 * sf, ((j + R) / NQ) ? par ^ 1u : par);
-                    q[(j + 2 * R) % NQ] = lds4(ctr_s + sf * C::CUR_BYTES);
+                    q[(j + 2 * R) % NQ] = lds4(ctr_s + sf * C::CUR_STRIDE);
                 } else {
                     q[(j + 2 * R) % NQ] = zero4();
                 }
                 // pointwise operands of plane i
-                const int sp = j % NPCC;
-                mbar_wait(bar_fp + 8 * sp, (((NQ / NPCC) & 1) ? par : 0u) ^ (uint32_t)((j / NPCC) & 1));
+                uint32_t pc;
+                if (C::PCT) {
+                    mbar_wait(bar_fp + 8 * (j % NPCC), par ^ (uint32_t)((j / NPCC) & 1));
+                    pc = pcc_t + (j % NPCC) * C::PCC_BYTES;
+                } else {
+                    mbar_wait(bar_fp + 8 * ps, pp);
+                    pc = pcc_t + ps * C::PCC_BYTES;
+                    if (++ps == NPCC) { ps = 0; pp ^= 1u; }
+                }
                 const int p = p_begin + i;
-                const float4 prev = lds4(pcc_t + sp * C::PCC_BYTES);
-                const float4 c2 = lds4(pcc_t + sp * C::PCC_BYTES + C::PL_BYTES);
-                const float4 c1 = (p >= blo_p && p < bhi_p) ? one4 : lds4(pcc_t + sp * C::PCC_BYTES + 2 * C::PL_BYTES);
+                const float4 prev = lds4(pc);
+                const float4 c2 = lds4(pc + C::PL_BYTES);
+                const float4 c1 = (p >= blo_p && p < bhi_p) ? one4 : lds4(pc + 2 * C::PL_BYTES);
                 float4 h1;
-                if (IMG == 2) h1 = lds4(pcc_t + sp * C::PCC_BYTES + 3 * C::PL_BYTES);
+                if (IMG == 2) h1 = lds4(pc + 3 * C::PL_BYTES);
                 // no z masking: beyond nz the TMA unit filled u[t], u[t-1] and c2 with zeros, so o == 0 there
-                const float4 o = point_update<R, 3, SW, false>(w, q, j, SAddr{ctr_s + (j % NCUR) * C::CUR_BYTES},
+                const float4 o = point_update<R, 3, SW, false>(w, q, j, SAddr{ctr_s + (j % NCUR) * C::CUR_STRIDE},
                                                                prev, c1, c2, 4);
                 // stage j (u[t] plane i) and the operand stage are free again
                 __syncwarp();
@@ -271,7 +286,6 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
             }
         }
     };
-    static_assert(((NQ / NPCC) & 1) == 1, "operand-ring parity formula assumes an odd number of ring turns per group");
     uint32_t par = 0;
     for (int pb = 0; pb < n_it; pb += NQ, par ^= 1u) {
         if (pb + NQ <= n_it && pb + NQ + R <= ncur) group(std::false_type{}, pb, par);
@@ -345,28 +359,42 @@ static const int g_tma = []() { const char *e = getenv("B2FWI_TMA"); return e ? 
 
 bool tma_step_supported(const Layout &L, const StepArgs &a, int img)
 {
-    if (L.ndim != 3 || !(img == 0 || img == 2) || L.halo != 0) return false;
+    if (L.ndim != 3 || !(img == 0 || img == 2) || L.halo != 0 || L.R < 1 || L.R > 8) return false;
     if (!(g_tma & (img == 0 ? 1 : 2))) return false;
     if (img == 2 && (!a.h1 || !a.grad || (((uintptr_t)a.h1 | (uintptr_t)a.grad) & 15))) return false;
-    if (!(L.R == 2 || L.R == 4)) return false;       // space_order 4 and 8
+    if (img == 2 && (a.illum || a.d2u)) return false;
     // TMA: 16-byte aligned base and strides (rows are pitched to 32 floats); float4 stores as in step_kernel
     const uintptr_t al = (uintptr_t)a.cur | (uintptr_t)a.prev | (uintptr_t)a.c1 | (uintptr_t)a.c2 | (uintptr_t)a.out;
     return (al & 15) == 0 && (L.sr % 4) == 0 && encode_fn() != nullptr;
 }
 
-// grid tile of the TMA kernel (pick_chunk sizes the plane chunks for it)
-void tma_tile_shape(int *tz, int *tr) { *tz = 128; *tr = 16; }
+// tile of the TMA kernels (pick_chunk sizes the plane chunks for whole waves of one CTA per SM)
+void tma_tile_shape(int R, int *tz, int *tr)
+{
+    *tz = (R <= 4) ? 128 : 64;
+    *tr = 16;
+}
+
+bool tma_enabled(int img) { return (g_tma & (img == 0 ? 1 : 2)) != 0 && encode_fn() != nullptr; }
+
+template <int R, int NPCC>
+static int launch_tma_r(const StepArgs &a, int img, cudaStream_t st)
+{
+    if (img == 2) return launch_tma<R, NPCC, 2, false>(a, st);
+    return (a.illum || a.d2u) ? launch_tma<R, NPCC, 0, true>(a, st) : launch_tma<R, NPCC, 0, false>(a, st);
+}
 
 int launch_step_tma(const Layout &L, const StepArgs &a, int img, cudaStream_t st)
 {
-    const bool extras = a.illum != nullptr || a.d2u != nullptr;
-    if (img == 2) {
-        if (extras) { set_error("imaging sweep with forward extras"); return B2FWI_EINVAL; }
-        return L.R == 2 ? launch_tma<2, 5, 2, false>(a, st) : launch_tma<4, 3, 2, false>(a, st);
-    }
     switch (L.R) {
-    case 2: return extras ? launch_tma<2, 5, 0, true>(a, st) : launch_tma<2, 5, 0, false>(a, st);
-    case 4: return extras ? launch_tma<4, 3, 0, true>(a, st) : launch_tma<4, 3, 0, false>(a, st);
+    case 1: return launch_tma_r<1, 3>(a, img, st);
+    case 2: return launch_tma_r<2, 5>(a, img, st);
+    case 3: return launch_tma_r<3, 3>(a, img, st);
+    case 4: return launch_tma_r<4, 3>(a, img, st);
+    case 5: return launch_tma_r<5, 3>(a, img, st);
+    case 6: return launch_tma_r<6, 3>(a, img, st);
+    case 7: return launch_tma_r<7, 3>(a, img, st);
+    case 8: return launch_tma_r<8, 3>(a, img, st);
     default: set_error("no TMA variant for stencil radius %d", L.R); return B2FWI_EUNSUPPORTED;
     }
 }

@@ -110,10 +110,11 @@ def test_forward_initial_state_time_window_and_scalar_vp():
 
 
 @pytest.mark.parametrize("so,shape", [(4, (34, 29, 38)), (8, (34, 29, 38)), (16, (34, 29, 38)),
-                                      (8, (33, 31, 37)), (4, (21, 40, 135))])
+                                      (8, (33, 31, 37)), (4, (21, 40, 135)), (2, (30, 29, 41)), (6, (29, 33, 38)),
+                                      (12, (31, 30, 70)), (16, (25, 37, 77))])
 def test_forward_gradient_3d(so, shape):
-    """so = 4 / 8 run the TMA-staged kernels, so = 16 the cp.async one; the odd shapes give partial float4
-    quads, a second (partial) z tile, partial row tiles and several plane chunks."""
+    """Every space order runs the TMA-staged kernels (128 z x 16 row tiles up to so = 8, 64 z x 16 above); the odd
+    shapes give partial float4 quads, a second (partial) z tile, partial row tiles and several plane chunks."""
     b = _b()
     nbl = 9
     vp = np.full(shape, 1.5, dtype=np.float32)
