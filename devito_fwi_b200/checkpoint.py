@@ -10,7 +10,8 @@ fit in HBM (3-D models).  Replaces pyrevolve / examples.checkpointing of the ref
 
 The forward kernels are deterministic, so the recomputed wavefield - and therefore the gradient -
 is bitwise identical to the one obtained from a full saved history (tests/test_gpu_parity.py).
-S ~ sqrt(2 * steps) minimises (2 * n_segments + S) slices of HBM.
+S ~ sqrt(2 * steps) minimises (2 * n_segments + S) slices of HBM. Whatever HBM is left after that is spent on
+keeping u.dt2 of further trailing segments from pass 1 (``keep_segments``), which are then not recomputed.
 
 ``forward(save='checkpoint')`` runs pass 1 while it records the receivers, and ``gradient(rec, u=<its result>)``
 then only needs pass 2: forward + recompute + adjoint = 3 sweeps per shot gradient instead of the 4 of the
@@ -40,25 +41,40 @@ class CheckpointedWavefield(object):
     data is not repeated (the reference's pyrevolve branch runs it a second time, wavesolver.py:188-201)."""
     save = None
 
-    def __init__(self, solver, src, vp_dev, coef, dt, nt, time_m, time_M, segs, ring, ckpt, segbuf):
+    def __init__(self, solver, src, vp_dev, coef, dt, nt, time_m, time_M, segs, ring, ckpt, segbuf, nkeep, S):
         self.solver, self.src, self.vp_dev, self.coef, self.dt = solver, src, vp_dev, coef, dt
         self.nt, self.time_m, self.time_M, self.segs = nt, time_m, time_M, segs
         self.ring, self.ckpt, self.segbuf = ring, ckpt, segbuf
+        self.nkeep, self.S = nkeep, S      # u.dt2 of the last nkeep segments is already in segbuf (S slices each)
 
     @property
     def nbytes(self):
         return sum(t.numel() * 4 for t in (self.ring, self.ckpt, self.segbuf))
 
 
+HBM_FRACTION = 0.75     # share of the free HBM that stored u.dt2 segments may take (the rest: v, grad, records)
+
+
+def _keep_segments(nseg, S, slice_bytes, reserve_slices=10):
+    """How many trailing segments can keep their u.dt2 from pass 1 (each one saves a recompute sweep of S steps
+    at the price of 4 B/pt more traffic in pass 1): as many as fit in HBM_FRACTION of what is free."""
+    import torch
+    free = torch.cuda.mem_get_info()[0] + torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+    budget = HBM_FRACTION * free - reserve_slices * slice_bytes
+    return int(max(1, min(nseg, budget // (S * slice_bytes))))
+
+
 def checkpointed_forward(solver, src, rec, vp, dt, illum=None, **kwargs):
     """Pass 1: forward sweep on a 3-slot ring with receiver recording (and the source illumination),
-    checkpointing the two live slices before every segment. Returns a CheckpointedWavefield."""
+    checkpointing the two live slices before every segment; the last ``keep_segments`` segments (default: as
+    many as HBM allows) store u.dt2 right away and are not recomputed by pass 2. Returns a CheckpointedWavefield."""
     import torch
     from .wavesolver import _ptr, _stream
     lib = _lib.lib()
     nt = min(rec.nt, src.nt) if rec is not None else src.nt
     time_m, time_M = solver._time_bounds(kwargs, nt)
     segs = plan_segments(time_m, time_M, kwargs.pop('segment', None))
+    keep = kwargs.pop('keep_segments', None)
     grid = solver.model.grid
     g = solver._gs()
     vp_dev = solver._vp_dev(vp)
@@ -73,16 +89,24 @@ def checkpointed_forward(solver, src, rec, vp, dt, illum=None, **kwargs):
     nseg = len(segs)
     S = max((tb - ta + 1) for ta, tb in segs) if segs else 1
     ckpt = torch.empty((max(nseg, 1), 2) + slice_shape, dtype=torch.float32, device='cuda')
-    segbuf = torch.empty((S,) + slice_shape, dtype=torch.float32, device='cuda')
+    nkeep = _keep_segments(nseg, S, grid.slice_elems * 4) if keep is None else max(1, min(int(keep), max(nseg, 1)))
+    try:
+        segbuf = torch.empty((nkeep * S,) + slice_shape, dtype=torch.float32, device='cuda')
+    except torch.cuda.OutOfMemoryError:
+        nkeep = 1
+        segbuf = torch.empty((S,) + slice_shape, dtype=torch.float32, device='cuda')
+    k0 = nseg - nkeep                      # first segment whose u.dt2 is kept
     cdt = ctypes.c_float(dt)
     for k, (ta, tb) in enumerate(segs):
-        ckpt[k, 0].copy_(ring[(ta - 1) % 3])
-        ckpt[k, 1].copy_(ring[ta % 3])
+        if k < k0:                          # kept segments are never restored: no checkpoint needed
+            ckpt[k, 0].copy_(ring[(ta - 1) % 3])
+            ckpt[k, 1].copy_(ring[ta % 3])
         _lib.check(lib.b2fwi_forward(
             ctypes.byref(g), _ptr(vp_dev), _ptr(coef), cdt, nt, ta, tb,
             _ptr(src_dev), src_map.byref(), _ptr(rec_dev), rec_map.byref() if rec_map is not None else None,
-            _ptr(ring), 0, _ptr(illum_dev), _ptr(segbuf) if k == nseg - 1 else None, ta, _stream()))
-    return CheckpointedWavefield(solver, src, vp_dev, coef, dt, nt, time_m, time_M, segs, ring, ckpt, segbuf)
+            _ptr(ring), 0, _ptr(illum_dev), _ptr(segbuf[(k - k0) * S:]) if k >= k0 else None, ta, _stream()))
+    return CheckpointedWavefield(solver, src, vp_dev, coef, dt, nt, time_m, time_M, segs, ring, ckpt, segbuf,
+                                 nkeep, S)
 
 
 def checkpointed_gradient(solver, rec, v, grad, vp, dt, checkpoints=None, **kwargs):
@@ -97,7 +121,8 @@ def checkpointed_gradient(solver, rec, v, grad, vp, dt, checkpoints=None, **kwar
         src = kwargs.pop('src', None) or solver.geometry.src
         nt_ = min(rec.nt, src.nt)
         tm, tM = solver._time_bounds(kwargs, nt_)
-        cw = checkpointed_forward(solver, src, None, vp, dt, time_m=tm, time_M=tM, segment=kwargs.pop('segment', None))
+        cw = checkpointed_forward(solver, src, None, vp, dt, time_m=tm, time_M=tM, segment=kwargs.pop('segment', None),
+                                  keep_segments=kwargs.pop('keep_segments', None))
         cw.nt = nt_
     nt, segs, ring, ckpt, segbuf = cw.nt, cw.segs, cw.ring, cw.ckpt, cw.segbuf
     grid = solver.model.grid
@@ -110,18 +135,22 @@ def checkpointed_gradient(solver, rec, v, grad, vp, dt, checkpoints=None, **kwar
     v_dev = v._buf.dev(write=True)
     grad_dev = grad._buf.dev(write=True)
     nseg = len(segs)
+    k0 = nseg - cw.nkeep
     cdt = ctypes.c_float(cw.dt)
     for k in range(nseg - 1, -1, -1):
         ta, tb = segs[k]
-        if k != nseg - 1:
+        if k >= k0:                         # u.dt2 kept from pass 1
+            hist = segbuf[(k - k0) * cw.S:]
+        else:                               # restore the checkpoint and recompute the segment (kept ones are consumed)
+            hist = segbuf
             ring[(ta - 1) % 3].copy_(ckpt[k, 0])
             ring[ta % 3].copy_(ckpt[k, 1])
             _lib.check(lib.b2fwi_forward(
                 ctypes.byref(g), _ptr(vp_dev), _ptr(coef), cdt, nt, ta, tb,
-                _ptr(src_dev), src_map.byref(), None, None, _ptr(ring), 0, None, _ptr(segbuf), ta, _stream()))
+                _ptr(src_dev), src_map.byref(), None, None, _ptr(ring), 0, None, _ptr(hist), ta, _stream()))
         _lib.check(lib.b2fwi_gradient(
             ctypes.byref(g), _ptr(vp_dev), _ptr(coef), cdt, nt, ta, tb,
-            _ptr(rec_dev), rec_map.byref(), _ptr(segbuf), 2, ta, _ptr(v_dev), _ptr(grad_dev), _stream()))
+            _ptr(rec_dev), rec_map.byref(), _ptr(hist), 2, ta, _ptr(v_dev), _ptr(grad_dev), _stream()))
     steps = max(cw.time_M - cw.time_m + 1, 0)
     bpp = BYTES_ADJ + (1 if checkpoints is not None else 2) * BYTES_FWD
     summary = solver._summary('Gradient', timer.stop(), steps, bpp)

@@ -144,7 +144,9 @@ def test_forward_gradient_3d(so, shape):
     print("3-D so=%d gradient rel-L2 %.2e" % (so, eg))
     assert eg <= TOL_GRAD
     # checkpoint + recompute must reproduce the full-history gradient bit for bit
-    grad_c, _ = solver.gradient(rec=residual, u=None, checkpointing=True, segment=7)
+    # (keep_segments=1: every segment but the last is restored and recomputed; default: as many u.dt2 segments
+    # as fit in HBM are kept from pass 1 - on this small grid all of them)
+    grad_c, _ = solver.gradient(rec=residual, u=None, checkpointing=True, segment=7, keep_segments=1)
     assert np.array_equal(grad_c.data, grad.data)
     grad_c2, _ = solver.gradient(rec=residual, u=None, checkpointing=True)
     assert np.array_equal(grad_c2.data, grad.data)
@@ -152,7 +154,8 @@ def test_forward_gradient_3d(so, shape):
     il_full = b.Function(name='il', grid=model.grid)
     solver.forward(save=True, illum=il_full)
     il_ck = b.Function(name='il', grid=model.grid)
-    d_ck, cw, _ = solver.forward(save='checkpoint', illum=il_ck, segment=5)
+    d_ck, cw, _ = solver.forward(save='checkpoint', illum=il_ck, segment=5, keep_segments=2)
+    assert cw.nkeep == 2 and len(cw.segs) > 3
     assert np.array_equal(d_ck.data, d.data)
     assert np.array_equal(il_ck.data, il_full.data)
     assert rel_l2(il_full.data, np.sum(u64 ** 2, axis=0)) <= TOL_GRAD
