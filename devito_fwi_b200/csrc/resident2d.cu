@@ -72,6 +72,39 @@ static __device__ __forceinline__ void cluster_barrier()
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---- halo exchange without a cluster-wide barrier (B2FWI_RES2D_ASYNC_HALO, default on)
+// The boundary rows travel as st.async stores that complete a transaction count on an mbarrier in the RECEIVING
+// CTA; a CTA then only waits for (a) its own threads (bar.sync) and (b) the bytes of its one or two neighbours.
+// barrier.cluster.arrive.release made every warp drain ALL its outstanding memory operations first - including the
+// streaming u.dt2 history stores to HBM (ncu: 8 % of the forward kernel in ERRBAR/membar, 10 % in the barrier wait).
+#ifndef B2FWI_RES2D_ASYNC_HALO
+#define B2FWI_RES2D_ASYNC_HALO 1
+#endif
+static __device__ __forceinline__ void st_async4(uint32_t remote_addr, float4 v, uint32_t remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(remote_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar) : "memory");
+}
+static __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+static __device__ __forceinline__ void mbar_arm(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t done, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();     // a lost halo would otherwise hang the GPU: fail loudly instead
+    } while (!done);
+}
+
 // Hide a value from the optimiser: stops ptxas/nvvm from strength-reducing the per-row addresses of the
 // unrolled row loop into P separately carried registers (which spilled the register-resident state).
 static __device__ __forceinline__ void opaque(uint32_t &x) { asm volatile("" : "+r"(x)); }
@@ -112,6 +145,7 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     float *injb = sxs + a.G * P;                                                // [2][RES2D_MAX_CELLS]
     float *cw_s = injb + 2 * RES2D_MAX_CELLS;                                   // [RES2D_MAX_CON] contribution weights
     unsigned short *cp_s = reinterpret_cast<unsigned short *>(cw_s + RES2D_MAX_CON);   // [RES2D_MAX_CON] point indices
+    const uint32_t hbar = smem_u32(cp_s + RES2D_MAX_CON);                       // [2] mbarriers: halo bytes of step parity
 
     for (int i = tid; i < 2 * tile_elems + a.rows_cta * wcols; i += blockDim.x) smem[i] = 0.f;
     for (int i = tid; i < a.G * P; i += blockDim.x) sxs[i] = (row0 + i < a.nx && i < rows_valid) ? a.sx[row0 + i] : 0.f;
@@ -194,6 +228,18 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
 
     const int nsteps = a.time_M - a.time_m + 1;
     const int t_first = (MODE == 0) ? a.time_m : a.time_M;
+    // halo bytes this CTA receives per step: R rows from the previous CTA, min(R, its valid rows) from the next
+    const int rows_next = min(a.rows_cta, a.nx - (crank + 1) * a.rows_cta);
+    const uint32_t halo_bytes = (uint32_t)(((crank > 0 ? R : 0) + (crank < a.C - 1 ? min(R, max(rows_next, 0)) : 0)) *
+                                           a.nzq * 16);
+    uint32_t prv_bar = 0, nex_bar = 0;      // the neighbours' mbarrier pair, through distributed shared memory
+    if (crank > 0) prv_bar = mapa_u32(hbar, crank - 1);
+    if (crank < a.C - 1) nex_bar = mapa_u32(hbar, crank + 1);
+    if (B2FWI_RES2D_ASYNC_HALO && tid == 0) {
+        mbar_init(hbar, 1);
+        mbar_init(hbar + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();      // cw_s / cp_s staged
     for (int s = tid; s < ncell; s += blockDim.x) injb[s] = gather(t_first, s);
     cluster.sync();
@@ -215,6 +261,7 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
         const uint32_t injc = inj_s + (uint32_t)(step & 1) * (RES2D_MAX_CELLS * 4u);
         float *injn = injb + ((step + 1) & 1) * RES2D_MAX_CELLS;
 
+        if (B2FWI_RES2D_ASYNC_HALO && tid == 0) mbar_arm(hbar + 8u * (step & 1), halo_bytes);
         // injection values of the NEXT step: loads in flight while this step computes
         const bool more = step + 1 < nsteps;
         const int t_next = (MODE == 0) ? t + 1 : t - 1;
@@ -344,8 +391,13 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                 if (f & 12u) {
                     const uint32_t off = own_off + (uint32_t)r * pitchB;
                     const float4 un = lds4(nxt_s + off);
+#if B2FWI_RES2D_ASYNC_HALO
+                    if (f & 4u) st_async4(prv_n + off + prev_delta, un, prv_bar + 8u * (step & 1));
+                    if (f & 8u) st_async4(nex_n + off - next_delta, un, nex_bar + 8u * (step & 1));
+#else
                     if (f & 4u) sts4_cluster(prv_n + off + prev_delta, un);
                     if (f & 8u) sts4_cluster(nex_n + off - next_delta, un);
+#endif
                 }
             }
         }
@@ -353,7 +405,12 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
             if (tid < ncell) injn[tid] = injv;
             for (int s = tid + blockDim.x; s < ncell; s += blockDim.x) injn[s] = gather(t_next, s);
         }
+#if B2FWI_RES2D_ASYNC_HALO
+        __syncthreads();                                              // this CTA's rows of u[t+1] (and the staging) are written
+        mbar_wait_cluster(hbar + 8u * (step & 1), (uint32_t)(step >> 1) & 1u);   // ... and the neighbours' boundary rows have landed
+#else
         cluster_barrier();
+#endif
         // swap buffers
         { uint32_t x = cur_s; cur_s = nxt_s; nxt_s = x; }
         { uint32_t x = prv_c; prv_c = prv_n; prv_n = x; }
@@ -361,6 +418,9 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
         hidx0 += hstep4;
     }
 
+#if B2FWI_RES2D_ASYNC_HALO
+    cluster.sync();       // no CTA leaves while a neighbour could still address its shared memory
+#endif
     // ---- window accumulator -> global
     if (a.out) {
         float *out = a.out + (int64_t)shot * (int64_t)(a.wx1 - a.wx0) * hq;
@@ -377,7 +437,8 @@ size_t res2d_smem_bytes(const Res2dArgs &a, int P)
     const size_t pitch = ((size_t)a.nzq + 2) * 4;
     const size_t wcols = (size_t)(a.wq1 - a.wq0) * 4;
     return sizeof(float) * (2 * (size_t)a.tile_rows * pitch + (size_t)a.rows_cta * wcols + (size_t)a.G * P +
-                            2 * RES2D_MAX_CELLS + RES2D_MAX_CON) + sizeof(unsigned short) * RES2D_MAX_CON;
+                            2 * RES2D_MAX_CELLS + RES2D_MAX_CON) + sizeof(unsigned short) * RES2D_MAX_CON +
+           2 * sizeof(unsigned long long);
 }
 
 template <int R, int P, int MODE>
