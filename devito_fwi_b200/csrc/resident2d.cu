@@ -262,6 +262,20 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
         float *injn = injb + ((step + 1) & 1) * RES2D_MAX_CELLS;
 
         if (B2FWI_RES2D_ASYNC_HALO && tid == 0) mbar_arm(hbar + 8u * (step & 1), halo_bytes);
+        if (MODE == 1 && has_hist && tid == 32 && step + 1 < nsteps && acc_rows > 0) {
+            // the history is streamed from HBM (5 GB per sweep, each value read once): one bulk L2 prefetch per step
+            // pulls this CTA's slab of the NEXT time level in, so the per-row loads below find it in L2
+            const float *nxt = a.hist + (int64_t)shot * a.hist_shot_stride +
+                               (int64_t)(t - 1 - a.hist_t0) * a.hist_t_stride + (int64_t)(row0 + acc_lr0 - a.wx0) * hq;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"((uint32_t)(acc_rows * hq * 4)) : "memory");
+        }
+        if (MODE == 1 && tid == 64 && crank == 0 && step + 2 < nsteps) {
+            // same for the residual row gathered at the top of the NEXT step (47 MB of residuals do not stay in L2
+            // next to the history stream): row t-2, widened to 16-byte bounds
+            const uintptr_t p0 = (uintptr_t)(vals + (int64_t)(t - 2) * a.nvals);
+            const uintptr_t lo = p0 & ~(uintptr_t)15, hi = (p0 + (uintptr_t)a.nvals * 4 + 15) & ~(uintptr_t)15;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
+        }
         // injection values of the NEXT step: loads in flight while this step computes
         const bool more = step + 1 < nsteps;
         const int t_next = (MODE == 0) ? t + 1 : t - 1;
