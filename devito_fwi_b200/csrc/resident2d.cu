@@ -93,12 +93,15 @@ static __device__ __forceinline__ void mbar_arm(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// (default .acquire.cta scope: the halo rows are written straight into this SM's shared memory before the byte count
+// completes, and shared memory is not cached - a cluster-scope acquire would only add an L1 invalidation
+// (CCTL.IVALL) per step, which throws away the L1-resident receiver maps)
 static __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 {
     uint32_t done, spins = 0;
     do {
         asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.b32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (!done && ++spins > (1u << 26)) __trap();     // a lost halo would otherwise hang the GPU: fail loudly instead
