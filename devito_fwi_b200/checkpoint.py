@@ -10,8 +10,8 @@ fit in HBM (3-D models).  Replaces pyrevolve / examples.checkpointing of the ref
 
 The forward kernels are deterministic, so the recomputed wavefield - and therefore the gradient -
 is bitwise identical to the one obtained from a full saved history (tests/test_gpu_parity.py).
-S ~ sqrt(2 * steps) minimises (2 * n_segments + S) slices of HBM. Whatever HBM is left after that is spent on
-keeping u.dt2 of further trailing segments from pass 1 (``keep_segments``), which are then not recomputed.
+S ~ sqrt(2 * steps) minimises (2 * n_segments + S) slices of HBM. Spare HBM can be spent on keeping u.dt2 of
+further trailing segments from pass 1 (``keep_segments=n`` or ``'auto'``), which are then not recomputed.
 
 ``forward(save='checkpoint')`` runs pass 1 while it records the receivers, and ``gradient(rec, u=<its result>)``
 then only needs pass 2: forward + recompute + adjoint = 3 sweeps per shot gradient instead of the 4 of the
@@ -66,8 +66,9 @@ def _keep_segments(nseg, S, slice_bytes, reserve_slices=10):
 
 def checkpointed_forward(solver, src, rec, vp, dt, illum=None, **kwargs):
     """Pass 1: forward sweep on a 3-slot ring with receiver recording (and the source illumination),
-    checkpointing the two live slices before every segment; the last ``keep_segments`` segments (default: as
-    many as HBM allows) store u.dt2 right away and are not recomputed by pass 2. Returns a CheckpointedWavefield."""
+    checkpointing the two live slices before every segment; the last ``keep_segments`` segments (default 1;
+    ``'auto'``: as many as fit in HBM_FRACTION of the free HBM) store u.dt2 right away and are not recomputed by
+    pass 2. Returns a CheckpointedWavefield."""
     import torch
     from .wavesolver import _ptr, _stream
     lib = _lib.lib()
@@ -89,7 +90,12 @@ def checkpointed_forward(solver, src, rec, vp, dt, illum=None, **kwargs):
     nseg = len(segs)
     S = max((tb - ta + 1) for ta, tb in segs) if segs else 1
     ckpt = torch.empty((max(nseg, 1), 2) + slice_shape, dtype=torch.float32, device='cuda')
-    nkeep = _keep_segments(nseg, S, grid.slice_elems * 4) if keep is None else max(1, min(int(keep), max(nseg, 1)))
+    if keep is None:
+        nkeep = 1                          # minimal footprint: only the last segment's u.dt2 comes from pass 1
+    elif keep == 'auto':
+        nkeep = _keep_segments(nseg, S, grid.slice_elems * 4)
+    else:
+        nkeep = max(1, min(int(keep), max(nseg, 1)))
     try:
         segbuf = torch.empty((nkeep * S,) + slice_shape, dtype=torch.float32, device='cuda')
     except torch.cuda.OutOfMemoryError:

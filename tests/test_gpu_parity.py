@@ -144,11 +144,11 @@ def test_forward_gradient_3d(so, shape):
     print("3-D so=%d gradient rel-L2 %.2e" % (so, eg))
     assert eg <= TOL_GRAD
     # checkpoint + recompute must reproduce the full-history gradient bit for bit
-    # (keep_segments=1: every segment but the last is restored and recomputed; default: as many u.dt2 segments
-    # as fit in HBM are kept from pass 1 - on this small grid all of them)
-    grad_c, _ = solver.gradient(rec=residual, u=None, checkpointing=True, segment=7, keep_segments=1)
+    # (default keep_segments=1: every segment but the last is restored and recomputed; 'auto': as many u.dt2
+    # segments as fit in HBM are kept from pass 1 - on this small grid all of them)
+    grad_c, _ = solver.gradient(rec=residual, u=None, checkpointing=True, segment=7)
     assert np.array_equal(grad_c.data, grad.data)
-    grad_c2, _ = solver.gradient(rec=residual, u=None, checkpointing=True)
+    grad_c2, _ = solver.gradient(rec=residual, u=None, checkpointing=True, keep_segments='auto')
     assert np.array_equal(grad_c2.data, grad.data)
     # forward(save='checkpoint') records the same data / illumination and hands its checkpoints to gradient()
     il_full = b.Function(name='il', grid=model.grid)
