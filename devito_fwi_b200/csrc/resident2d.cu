@@ -288,6 +288,21 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
             for (int j = gj0; j < gj1; j++) injv = fmaf(cw_s[j], __ldg(vrow + cp_s[j]), injv);
         }
 
+        // B / history of the first two rows: issued first, so that their L2 latency runs under the recording below
+        // and the window fill instead of stalling row 0
+        uint32_t hp = hidx0;
+        uint32_t bp = Bidx0;
+        opaque(bp);
+        float4 bpre[2], hpre[2];
+        if (tactive) {
+            if (flags & 0x01ull) bpre[0] = ldg_stream4(Bbase + bp);
+            if (P > 1 && (flags & 0x10ull)) bpre[1] = ldg_stream4(Bbase + (bp + Bstride));
+            if (MODE == 1) {
+                if (flags & 0x02ull) hpre[0] = ldg_stream4(hbase + hp);
+                if (P > 1 && (flags & 0x20ull)) hpre[1] = ldg_stream4(hbase + (hp + hq4));
+            }
+        }
+
         if (MODE == 0 && a.rec) {
             // rec[t][p] = sum_c w_c u[t][c]   (operators.py:137)
             const int cnt = a.itp_desc[2 * sc], base = a.itp_desc[2 * sc + 1];
@@ -312,16 +327,6 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
             uint32_t ro = cur_s + own_off;                             // own row, current buffer
             uint32_t rn = nxt_s + own_off;                             // own row, next buffer
             uint32_t ra = acc_s0;
-            uint32_t hp = hidx0;
-            uint32_t bp = Bidx0;
-            opaque(bp);
-            float4 bpre[2], hpre[2];
-            if (flags & 0x01ull) bpre[0] = ldg_stream4(Bbase + bp);
-            if (P > 1 && (flags & 0x10ull)) bpre[1] = ldg_stream4(Bbase + (bp + Bstride));
-            if (MODE == 1) {
-                if (flags & 0x02ull) hpre[0] = ldg_stream4(hbase + hp);
-                if (P > 1 && (flags & 0x20ull)) hpre[1] = ldg_stream4(hbase + (hp + hq4));
-            }
 #pragma unroll
             for (int r = 0; r < P; r++) {
                 w[(r + 2 * R) % NW] = lds4(rw);
