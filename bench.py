@@ -42,38 +42,69 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    """SM clock / throttle reasons while the timed regions run: NVML every 10 ms (nvidia_ml_py), else nvidia-smi
+    every 200 ms."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.rows = []              # (sm_mhz, [reason flags]) per sample
+        self.sm_max = None
+        self.source = None
         self.stop_flag = threading.Event()
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it holds plain indices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.index
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            idx = int(vis.split(",")[self.index])
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        masks = [0x8, 0x40, 0x20, 0x4]      # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
+        self.source = "nvml"
+        while not self.stop_flag.is_set():
+            r = int(get_reasons(h))
+            self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), [bool(r & m) for m in masks]))
+            self.stop_flag.wait(0.01)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
                                      stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                    c = [x.strip() for x in out.split(",")]
+                    self.sm_max = float(c[2])
+                    self.rows.append((float(c[1]), [c[5 + k].lower().startswith("active") for k in range(4)]))
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[1]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[5 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]), "reasons": reasons,
-                "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for k, n in enumerate(self.NAMES) if any(r[1][k] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(self.rows), "source": self.source}
 
 
 def make_survey(world):
