@@ -212,7 +212,11 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     };
     // contribution range of the slot this thread gathers every step (slot == tid)
     int gj0 = 0, gj1 = 0;
-    if (tid < ncell) { gj0 = a.inj_cptr[cell_base + tid] - con0; gj1 = a.inj_cptr[cell_base + tid + 1] - con0; }
+    // "service" roles (injection gather, receiver recording) are dealt out from the middle of the CTA: the first and
+    // last warps own the boundary strips and already carry the halo pushes
+    const int svc0 = ((int)blockDim.x / 3) & ~31;
+    const int stid = (tid >= svc0) ? tid - svc0 : tid + (int)blockDim.x - svc0;
+    if (stid < ncell) { gj0 = a.inj_cptr[cell_base + stid] - con0; gj1 = a.inj_cptr[cell_base + stid + 1] - con0; }
 
     // ---- 32-bit shared addresses (bytes); everything below is an offset from these
     const uint32_t pitchB = (uint32_t)pitch * 4u;
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
         if (MODE == 0 && a.rec) {
             // rec[t][p] = sum_c w_c u[t][c]   (operators.py:137)
             const int cnt = a.itp_desc[2 * sc], base = a.itp_desc[2 * sc + 1];
-            for (int i = tid; i < cnt; i += blockDim.x) {
+            for (int i = stid; i < cnt; i += blockDim.x) {
                 float sum = 0.f;
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
@@ -424,8 +428,8 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
             }
         }
         if (more) {
-            if (tid < ncell) injn[tid] = injv;
-            for (int s = tid + blockDim.x; s < ncell; s += blockDim.x) injn[s] = gather(t_next, s);
+            if (stid < ncell) injn[stid] = injv;
+            for (int s = stid + blockDim.x; s < ncell; s += blockDim.x) injn[s] = gather(t_next, s);
         }
 #if B2FWI_RES2D_ASYNC_HALO
         __syncthreads();                                              // this CTA's rows of u[t+1] (and the staging) are written
