@@ -178,9 +178,16 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
         }
     }
     const float4 szq = tactive ? __ldg(reinterpret_cast<const float4 *>(a.sz + 4 * qi)) : z4();
+    // rows pushed to the neighbours. Forward kernel: a compact mask (bit r: to the previous CTA, bit 16+r: to the
+    // next), walked bit by bit; the backward kernel has no register to spare for it and tests the flags instead.
+    unsigned pmask = 0;
     bool push_any = false;
 #pragma unroll
-    for (int r = 0; r < P; r++) push_any = push_any || (((flags >> (4 * r)) & 12ull) != 0ull);
+    for (int r = 0; r < P; r++) {
+        if ((flags >> (4 * r)) & 4ull) pmask |= 1u << r;
+        if ((flags >> (4 * r)) & 8ull) pmask |= 0x10000u << r;
+        push_any = push_any || (((flags >> (4 * r)) & 12ull) != 0ull);
+    }
     // injection cells owned by this thread are rare: only the row bitmap lives in a register, the lane mask and the
     // first slot index are re-read from global memory (L1/L2) inside the rarely taken branch
     const unsigned long long *imask_p = a.thr_mask + (int64_t)sc * T + tid;
@@ -410,7 +417,26 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
         // push this CTA's R boundary rows into the neighbours' halo rows (distributed shared memory). Done after the
         // row loop, by the few threads that own boundary rows, re-reading what they just wrote: keeps the ~10
         // address-conversion instructions of a remote store out of every row of every thread.
-        if (push_any) {
+        if (MODE == 0) {
+            for (unsigned m = pmask & 0xffffu; m; m &= m - 1) {
+                const uint32_t off = own_off + (uint32_t)(__ffs(m) - 1) * pitchB;
+                const float4 un = lds4(nxt_s + off);
+#if B2FWI_RES2D_ASYNC_HALO
+                st_async4(prv_n + off + prev_delta, un, prv_bar + 8u * (step & 1));
+#else
+                sts4_cluster(prv_n + off + prev_delta, un);
+#endif
+            }
+            for (unsigned m = pmask >> 16; m; m &= m - 1) {
+                const uint32_t off = own_off + (uint32_t)(__ffs(m) - 1) * pitchB;
+                const float4 un = lds4(nxt_s + off);
+#if B2FWI_RES2D_ASYNC_HALO
+                st_async4(nex_n + off - next_delta, un, nex_bar + 8u * (step & 1));
+#else
+                sts4_cluster(nex_n + off - next_delta, un);
+#endif
+            }
+        } else if (push_any) {
 #pragma unroll
             for (int r = 0; r < P; r++) {
                 const unsigned f = (unsigned)(flags >> (4 * r)) & 0xFu;
