@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     int gj0 = 0, gj1 = 0;
     // "service" roles (injection gather, receiver recording) are dealt out from the middle of the CTA: the first and
     // last warps own the boundary strips and already carry the halo pushes
-    const int svc0 = ((int)blockDim.x / 3) & ~31;
+    const int nsvc = (MODE == 0 && a.rec) ? max(ncell, a.itp_desc[2 * sc]) : ncell;      // busiest service role
+    const int svc0 = (max((int)blockDim.x - ((nsvc + 31) & ~31), 0) / 2) & ~31;          // ... centred in the CTA
     const int stid = (tid >= svc0) ? tid - svc0 : tid + (int)blockDim.x - svc0;
     if (stid < ncell) { gj0 = a.inj_cptr[cell_base + stid] - con0; gj1 = a.inj_cptr[cell_base + stid + 1] - con0; }
 
