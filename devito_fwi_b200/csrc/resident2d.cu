@@ -5,8 +5,9 @@
 // points: one wavefield is ~300 KB, so a time step is bound by launch / synchronisation latency, not by
 // HBM. This engine therefore keeps, per shot, on the C SMs of a cluster:
 //   * u[t] in shared memory, double buffered, rows split across the cluster's CTAs; the R boundary rows
-//     are pushed into the neighbour CTA's halo rows through distributed shared memory (st.shared::cluster)
-//     and one barrier.cluster per time step orders everything;
+//     are pushed into the neighbour CTA's halo rows through distributed shared memory as st.async stores that
+//     complete a byte count on an mbarrier of the receiving CTA: per step a CTA waits for its own threads
+//     (bar.sync) and for its neighbours' bytes, there is no cluster-wide barrier;
 //   * per grid point, in REGISTERS: delta = u[t] - u[t-1] (the update is carried in increment form) and
 //     B = dt^2 vp^2; each thread owns a strip of P rows x 4 contiguous z and streams a 2R+1-row register
 //     window down its strip (2.5-D register streaming along the slow axis, 128-bit shared loads along z);
@@ -14,7 +15,8 @@
 //   * source / residual injection through a cell-centric gather staged in shared memory one step ahead,
 //     receiver interpolation straight from the shared tile;
 //   * the zero-lag imaging condition (backward) and the source illumination (forward) accumulate in a
-//     shared-memory tile of the imaging window; only u.dt2 of that window streams to / from HBM.
+//     shared-memory tile of the imaging window; only u.dt2 of that window streams to / from HBM (backward: one
+//     bulk L2 prefetch per step pulls the next time level's slab in ahead of the per-row loads).
 // Update (same algebra as operators.py:87 / acoustic_time_update_nb.ipynb cell 3, written for delta):
 //   delta+ = c1 * (delta + B * L(u)),  u+ = u + delta+,  c1 = 1/(1 + (damp/dt) * B),  c2 = B * c1.
 // All shots of a rank run concurrently (grid = nshots clusters); arithmetic uses packed fp32x2 FMAs.
