@@ -321,3 +321,26 @@ def test_born_adjoint_and_linearisation(ndim):
         errs.append(np.linalg.norm(lin) / np.linalg.norm(eps * np.float64(du.data)))
     print("   linearisation error at eps=0.5, 0.25: %.3e %.3e" % tuple(errs))
     assert errs[1] < 0.6 * errs[0] and errs[1] < 0.1          # first-order remainder: halves with eps
+
+
+def test_fwi_objective_with_checkpointing_2d():
+    """fwi_obj_single through the per-shot streaming engine: the checkpointed branch (taken automatically when the
+    saved history would not fit in HBM) must reproduce the saved-history objective, gradient and illumination."""
+    b = _b()
+    from devito_fwi_b200 import configs, fwi
+    g_true, g_init, g_const, _ = configs.marmousi(nsrc=3, tn=1500.)
+    fwi.ENGINE = 'stream'
+    try:
+        obs = fwi.fm_multi(g_true)
+        dw = fwi.fm_multi(g_const)
+        gi = fwi._shot_geometry(g_init, 1)
+        fwi.CHECKPOINT = False
+        f0, g0, r0, i0 = fwi.fwi_obj_single(gi, obs[1], fwi.least_square, dw[1], calc_grad=True)
+        fwi.CHECKPOINT = True
+        f1, g1, r1, i1 = fwi.fwi_obj_single(gi, obs[1], fwi.least_square, dw[1], calc_grad=True)
+    finally:
+        fwi.ENGINE = 'auto'
+        fwi.CHECKPOINT = None
+    assert f0 == f1 and np.array_equal(np.asarray(r0), np.asarray(r1))
+    assert np.array_equal(g0, g1) and np.array_equal(i0, i1)
+    assert np.abs(g0).max() > 0 and np.abs(i0).max() > 0
