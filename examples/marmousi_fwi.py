@@ -87,15 +87,22 @@ def main():
     toc = time.time()
     if rank0:
         vp = 1.0 / np.sqrt(m.reshape(shape))
-        err0 = np.linalg.norm(1. / np.sqrt(m0.reshape(shape)) - vp_true) / np.linalg.norm(vp_true)
-        err1 = np.linalg.norm(vp - vp_true) / np.linalg.norm(vp_true)
+        vp0 = 1. / np.sqrt(m0.reshape(shape))
+
+        def rel_err(v, region):
+            return np.linalg.norm((v - vp_true)[region]) / np.linalg.norm(vp_true[region])
+        nx, nz = shape
+        regions = [("whole model", (slice(None), slice(None))),
+                   ("well illuminated (central 80 % in x, upper 40 % in z)", (slice(nx // 10, nx - nx // 10), slice(7, (2 * nz) // 5))),
+                   ("deep part (lower 35 % in z)", (slice(None), slice((65 * nz) // 100, None)))]
         os.makedirs(args.odir, exist_ok=True)
         vp.astype(np.float32).tofile(os.path.join(args.odir, "marmousi_result_misfit_0"))
         print("driver: %s | %d objective evaluations in %.2f s on %d GPU(s)" % (driver, len(history), toc - tic,
                                                                               dist.world_size()))
         if f_start is not None:
             print("objective %.4e -> %.4e" % (f_start, f_end))
-        print("relative model error vs true vp: %.4f -> %.4f" % (err0, err1))
+        for name, region in regions:
+            print("relative model error vs true vp, %s: %.4f -> %.4f" % (name, rel_err(vp0, region), rel_err(vp, region)))
     return history
 
 
