@@ -90,6 +90,12 @@ def partition_shots(grid, space_order, nbl, nshots):
         if rc != 0 or n.value <= 0:
             continue
         cands.append((plan.rows_cta * (1.0 + 0.02 * plan.cluster) + 60.0, int(n.value), int(plan.cluster)))
+    return best_partition(cands, nshots)
+
+
+def best_partition(cands, nshots):
+    """``cands``: [(cost of one wave, resident clusters, cluster size)]; returns [(count, cluster), ...] covering
+    ``nshots`` at minimum total cost: best(n) = min_p cost_p + best(n - min(n, slots_p))."""
     if not cands:
         return None
     memo = {}

@@ -107,3 +107,30 @@ def test_shot_partition():
     assert sorted(sum(shots, [])) == list(range(29))
     assert max(map(len, shots)) - min(map(len, shots)) <= 1
     assert dist.local_shots(29) == list(range(29))
+
+
+def test_launch_group_partition_logic():
+    """resident.best_partition: surveys with more shots than resident clusters are cut into launch groups."""
+    from devito_fwi_b200.resident import best_partition
+    # Marmousi-like candidates: (cost of one wave, clusters resident at once, cluster size)
+    cands = [(95 * 1.08 + 60, 33, 4), (76 * 1.10 + 60, 26, 5), (64 * 1.12 + 60, 22, 6), (48 * 1.16 + 60, 14, 8)]
+    assert best_partition(cands, 29) == [(29, 4)]                    # one wave of the smallest cluster that holds them
+    assert best_partition(cands, 5) == [(5, 8)]                      # few shots: the widest cluster
+    assert best_partition(cands, 26) == [(26, 5)]
+    # more than one wave: a full wave of 5-CTA clusters + the remainder on 8-CTA clusters (259) beats 33 x 4 + 7 x 8 (278)
+    assert best_partition(cands, 40) == [(26, 5), (14, 8)]
+    for n in (1, 13, 14, 15, 66, 67, 300):
+        g = best_partition(cands, n)
+        assert sum(k for k, _ in g) == n and all(k <= dict((c, s) for _, s, c in cands)[c] for k, c in g)
+    assert best_partition([], 3) is None
+
+
+def test_checkpoint_segment_plan():
+    from devito_fwi_b200.checkpoint import plan_segments
+    segs = plan_segments(1, 688)
+    assert segs[0][0] == 1 and segs[-1][1] == 688
+    assert all(a2 == b1 + 1 for (_, b1), (a2, _) in zip(segs, segs[1:]))          # contiguous, no overlap
+    S = segs[0][1] - segs[0][0] + 1
+    assert S == 38 and len(segs) == 19                                             # ~sqrt(2 * 688)
+    assert plan_segments(5, 4) == [] and plan_segments(3, 3) == [(3, 3)]
+    assert plan_segments(1, 10, segment=4) == [(1, 4), (5, 8), (9, 10)]
