@@ -121,9 +121,13 @@ struct MaxThreads { static constexpr int value = (P <= 8) ? 480 : (P <= 12) ? 38
 
 // MODE 0: forward (record receivers, store u.dt2 history, accumulate illumination)
 // MODE 1: backward with imaging condition (read u.dt2 history, accumulate gradient)
-template <int R, int P, int MODE>
+// MODE 2: forward of a gradient evaluation - history AND illumination are known to be requested, which removes the two
+//         loop-invariant pointer tests from every row (the compiler re-tests them per row to save predicate registers)
+template <int R, int P, int MODE_>
 __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __grid_constant__ Res2dArgs a)
 {
+    constexpr int MODE = (MODE_ == 2) ? 0 : MODE_;
+    constexpr bool SAVE = (MODE_ == 2);
     extern __shared__ __align__(16) float smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                             (int64_t)(row0 + lr0 - a.wx0) * hq + 4 * (qi - a.wq0)) / 4);
     const uint32_t hstep4 = (uint32_t)(((MODE == 0) ? a.hist_t_stride : -a.hist_t_stride) / 4);   // wraps mod 2^32
     const float c0 = a.c0, c0_lo = a.c0_lo, inv_dt2 = a.inv_dt2;
-    const bool has_hist = a.hist != nullptr;
+    const bool has_hist = SAVE || a.hist != nullptr;
 
     for (int step = 0; step < nsteps; ++step) {
         const int t = (MODE == 0) ? a.time_m + step : a.time_M - step;
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
                                 const float4 d2 = mul4s(inv_dt2, add4(dn, make_float4(-dl[r].x, -dl[r].y, -dl[r].z, -dl[r].w)));
                                 __stcs(hbase + hp, d2);
                             }
-                            if (a.out) sts4(ra, fma4(un, un, lds4(ra)));            // illum += u[t+1]^2
+                            if (SAVE || a.out) sts4(ra, fma4(un, un, lds4(ra)));    // illum += u[t+1]^2
                         }
                     }
                     dl[r] = dn;
@@ -572,7 +576,8 @@ int launch_res2d(const Res2dArgs &a, int R, int P, int mode, cudaStream_t st)
     }
 #define B2_RCASE(r)                                                         \
     case r:                                                                 \
-        return mode == 0 ? launch_P<r, 0>(a, P, st) : launch_P<r, 1>(a, P, st);
+        return mode != 0 ? launch_P<r, 1>(a, P, st)                         \
+                         : (a.hist && a.out) ? launch_P<r, 2>(a, P, st) : launch_P<r, 0>(a, P, st);
     switch (R) {
         B2_RCASE(2) B2_RCASE(3) B2_RCASE(4)
     default: set_error("res2d: space order %d not supported by the resident engine", 2 * R); return B2FWI_EUNSUPPORTED;
