@@ -275,3 +275,22 @@ def test_observed_data_cache_follows_host_modifications():
     obs2 = fwi.fm_multi(g_true)                  # a different list object with the original data
     f3, _, _ = fwi.fwi_obj_multi(g_init, obs2, fwi.least_square, None, None, False, False)
     assert np.isclose(f3, f1, rtol=1e-12)
+
+
+def test_objective_with_observed_data_on_another_time_axis():
+    """fwi.py:47-57 / source.py:140-170: observed data recorded at another sampling step are
+    spline-resampled onto the modelling axis inside the objective (the per-shot streaming branch, not the batched
+    one). Up-sampling the records to dt/2 keeps every original sample as a spline node, so the objective and gradient
+    must come out the same as with the original records."""
+    from devito_fwi_b200 import configs, fwi
+    g_true, g_init, g_const, mask = configs.marmousi(nsrc=2, tn=1200.)
+    x = (1. / (g_init.model.vp.data[40:-40, 40:-40].astype(np.float64) ** 2)).ravel()
+    obs, dw = fwi.fm_multi(g_true), fwi.fm_multi(g_const)
+    f1, g1, _ = fwi.fwi_loss(x, g_init, obs, fwi.least_square, dw, mask, True, True)
+    dt = float(g_init.dt)
+    obs_fine = [o.resample(dt=dt / 2) for o in obs]
+    assert obs_fine[0].data.shape[0] == 2 * (g_init.nt - 1) + 1
+    f2, g2, res2 = fwi.fwi_loss(x, g_init, obs_fine, fwi.least_square, dw, mask, True, True)
+    assert len(res2) == 2 and np.asarray(res2[0]).shape == (g_init.nt, 300)
+    print("resampled observed data: f %.3e g %.3e" % (abs(f2 - f1) / f1, rel_l2(g2, g1)))
+    assert abs(f2 - f1) <= 1e-4 * f1 and rel_l2(g2, g1) <= 2 * TOL_GRAD
