@@ -94,6 +94,7 @@ PROTOTYPES = {
     "b2fwi_version": (_I, []),
     "b2fwi_last_error": (ctypes.c_char_p, []),
     "b2fwi_launch_count": (ctypes.c_int64, []),
+    "b2fwi_set_option": (ctypes.c_int, [ctypes.c_char_p, _I]),
     "b2fwi_field_layout": (ctypes.c_int, [_G, ctypes.POINTER(ctypes.c_int64 * 3),
                                           ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "b2fwi_prepare_coeffs": (ctypes.c_int, [_G, _P, _P, _F, _P, _P]),

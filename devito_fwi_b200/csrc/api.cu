@@ -111,6 +111,18 @@ const char *b2fwi_last_error(void) { return g_err; }
 
 int64_t b2fwi_launch_count(void) { return (int64_t)g_launches.load(); }
 
+int b2fwi_set_option(const char *name, int32_t value)
+{
+    B2_CHECK_ARG(name != nullptr, "option name is NULL");
+    if (strcmp(name, "tma") == 0) {
+        const int old = get_tma_mask();
+        set_tma_mask(value);
+        return old;
+    }
+    set_error("unknown option '%s'", name);
+    return B2FWI_EINVAL;
+}
+
 int b2fwi_field_layout(const b2fwi_grid *g, int64_t stride_out[3], int64_t *base_out, int64_t *elems_out)
 {
     Layout L;

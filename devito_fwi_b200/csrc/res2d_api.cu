@@ -14,7 +14,8 @@ int res2d_max_clusters(const Res2dArgs &a, int R, int P, int *out);
 
 static const int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
 
-static int max_threads_for(int P) { return P <= 8 ? 480 : P <= 12 ? 384 : 288; }
+static int max_threads_for(int P) { return P <= 4 ? 512 : P <= 8 ? 480 : P <= 12 ? 384 : 288; }
+static const int kMaxCluster = 16;     // 9..16 = non-portable cluster sizes (cudaFuncAttributeNonPortableClusterSizeAllowed)
 
 __global__ void bcoef_kernel(const float *__restrict__ vp, double dt, float *__restrict__ B, int64_t n)
 {
@@ -240,7 +241,7 @@ static int fill_args(const b2fwi_grid *g, const b2fwi_res2d_plan *p, Res2dArgs *
     a->c0 = w.c0; a->c0_lo = w.c0_lo;
     for (int k = 0; k <= 4; k++) { a->cx[k] = w.cr[k]; a->cz[k] = w.cz[k]; }
     // consistency of the plan with the grid
-    B2_CHECK_ARG(a->C >= 1 && a->C <= 8, "cluster size %d", a->C);
+    B2_CHECK_ARG(a->C >= 1 && a->C <= kMaxCluster, "cluster size %d", a->C);
     B2_CHECK_ARG(a->rows_cta * a->C >= a->nx && a->rows_cta * (a->C - 1) < a->nx, "rows_cta %d does not tile nx %d",
                  a->rows_cta, a->nx);
     B2_CHECK_ARG(a->nx - a->rows_cta * (a->C - 1) >= L.R, "last CTA has fewer than R rows");
@@ -280,12 +281,14 @@ int b2fwi_res2d_plan_model(const b2fwi_grid *g, int32_t nbl, int32_t min_cluster
     const int nx = g->shape[0], nz = g->shape[1], nzq = (nz + 3) / 4;
     B2_CHECK_ARG(nbl >= 0 && 2 * nbl < nx && 2 * nbl < nz, "bad nbl %d", nbl);
     if (min_cluster < 1) min_cluster = 1;
-    const int Ps[3] = {8, 12, 16};
-    for (int C = min_cluster; C <= 8; C++) {
+    // rows per thread: the smallest strip whose thread count fits (more warps per SM hide the dependent chain of a
+    // row better; longer strips only amortise the 2R-row window fill)
+    const int Ps[4] = {4, 8, 12, 16};
+    for (int C = min_cluster; C <= kMaxCluster; C++) {
         const int rows_cta = (nx + C - 1) / C;
         if (rows_cta * (C - 1) >= nx) continue;
         if (nx - rows_cta * (C - 1) < L.R || rows_cta < 2 * L.R) continue;
-        for (int ip = 0; ip < 3; ip++) {
+        for (int ip = 0; ip < 4; ip++) {
             const int P = Ps[ip];
             const int G = (rows_cta + P - 1) / P;
             const int threads = (nzq * G + 31) / 32 * 32;
@@ -302,7 +305,7 @@ int b2fwi_res2d_plan_model(const b2fwi_grid *g, int32_t nbl, int32_t min_cluster
             return 0;
         }
     }
-    set_error("resident engine: grid %dx%d (space_order %d) does not fit a cluster of <= 8 SMs", nx, nz, g->space_order);
+    set_error("resident engine: grid %dx%d (space_order %d) does not fit a cluster of <= 16 SMs", nx, nz, g->space_order);
     return B2FWI_EUNSUPPORTED;
 }
 

@@ -117,7 +117,7 @@ template <typename T>
 static __device__ __forceinline__ void opaque_ptr(T *&p) { asm volatile("" : "+l"(p)); }
 
 template <int P>
-struct MaxThreads { static constexpr int value = (P <= 8) ? 480 : (P <= 12) ? 384 : 288; };
+struct MaxThreads { static constexpr int value = (P <= 4) ? 512 : (P <= 8) ? 480 : (P <= 12) ? 384 : 288; };
 
 // MODE 0: forward (record receivers, store u.dt2 history, accumulate illumination)
 // MODE 1: backward with imaging condition (read u.dt2 history, accumulate gradient)
@@ -506,6 +506,7 @@ static int launch_one(const Res2dArgs &a, cudaStream_t st)
     const size_t smem = res2d_smem_bytes(a, P);
     auto kern = res2d_kernel<R, P, MODE>;
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (a.C > 8) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));   // up to 16 SMs per shot
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(a.nshots * a.C), 1, 1);
@@ -528,6 +529,7 @@ template <int R, int MODE>
 static int launch_P(const Res2dArgs &a, int P, cudaStream_t st)
 {
     switch (P) {
+    case 4: return launch_one<R, 4, MODE>(a, st);
     case 8: return launch_one<R, 8, MODE>(a, st);
     case 12: return launch_one<R, 12, MODE>(a, st);
     case 16: return launch_one<R, 16, MODE>(a, st);
@@ -541,6 +543,7 @@ static int max_clusters_one(const Res2dArgs &a, int *out)
     const size_t smem = res2d_smem_bytes(a, P);
     auto kern = res2d_kernel<R, P, 0>;
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (a.C > 8) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(a.C * 64), 1, 1);
@@ -561,8 +564,8 @@ static int max_clusters_one(const Res2dArgs &a, int *out)
 int res2d_max_clusters(const Res2dArgs &a, int R, int P, int *out)
 {
 #define B2_OCASE(r, p) if (R == r && P == p) return max_clusters_one<r, p>(a, out);
-    B2_OCASE(2, 8) B2_OCASE(2, 12) B2_OCASE(2, 16) B2_OCASE(3, 8) B2_OCASE(3, 12) B2_OCASE(3, 16)
-    B2_OCASE(4, 8) B2_OCASE(4, 12) B2_OCASE(4, 16)
+    B2_OCASE(2, 4) B2_OCASE(2, 8) B2_OCASE(2, 12) B2_OCASE(2, 16) B2_OCASE(3, 4) B2_OCASE(3, 8) B2_OCASE(3, 12)
+    B2_OCASE(3, 16) B2_OCASE(4, 4) B2_OCASE(4, 8) B2_OCASE(4, 12) B2_OCASE(4, 16)
 #undef B2_OCASE
     set_error("res2d: unsupported (R, P) = (%d, %d)", R, P);
     return B2FWI_EUNSUPPORTED;
@@ -570,7 +573,7 @@ int res2d_max_clusters(const Res2dArgs &a, int R, int P, int *out)
 
 int launch_res2d(const Res2dArgs &a, int R, int P, int mode, cudaStream_t st)
 {
-    if (a.threads > (P <= 8 ? 480 : P <= 12 ? 384 : 288)) {
+    if (a.threads > (P <= 4 ? 512 : P <= 8 ? 480 : P <= 12 ? 384 : 288)) {
         set_error("res2d: %d threads exceed the limit for P=%d", a.threads, P);
         return B2FWI_EINVAL;
     }

@@ -33,6 +33,8 @@ bool tma_step_supported(const Layout &L, const StepArgs &a, int img);
 int launch_step_tma(const Layout &L, const StepArgs &a, int img, cudaStream_t st);
 void tma_tile_shape(int R, int *tz, int *tr);
 bool tma_enabled(int img);
+void set_tma_mask(int mask);      // b2fwi_set_option("tma", mask): bit 0 forward, bit 1 adjoint + imaging
+int get_tma_mask();
 int launch_inject(float *field, const float *vp, float dt, const float *vals, const b2fwi_sparse *m,
                   float *d2u, const float *cur, const float *prev, float inv_dt2, cudaStream_t st);
 int launch_interp(const float *field, float *out, const b2fwi_sparse *m, cudaStream_t st);

@@ -355,7 +355,9 @@ static int launch_tma(const StepArgs &a, cudaStream_t st)
 }
 
 // B2FWI_TMA: bit 0 forward sweep, bit 1 adjoint + imaging sweep (A/B against the register-staged kernels)
-static const int g_tma = []() { const char *e = getenv("B2FWI_TMA"); return e ? atoi(e) : 3; }();
+static int g_tma = []() { const char *e = getenv("B2FWI_TMA"); return e ? atoi(e) : 3; }();
+void set_tma_mask(int mask) { g_tma = mask & 3; }
+int get_tma_mask() { return g_tma; }
 
 bool tma_step_supported(const Layout &L, const StepArgs &a, int img)
 {

@@ -20,6 +20,7 @@ __all__ = ['ResidentSurvey', 'plan_model']
 
 MAX_CELLS = 1024      # RES2D_MAX_CELLS
 MAX_CON = 1024        # RES2D_MAX_CON (contributions per CTA; point indices are staged as uint16)
+MAX_CLUSTER = 16      # CTAs (SMs) per shot; 9..16 are non-portable cluster sizes
 
 
 class Plan(ctypes.Structure):
@@ -52,7 +53,7 @@ def choose_plan(grid, space_order, nbl, nshots):
     smallest cluster that fits. Uses cudaOccupancyMaxActiveClusters through the C ABI."""
     g = grid_struct(grid, space_order)
     best, best_cost, seen = None, None, set()
-    for cmin in range(1, 9):
+    for cmin in range(1, MAX_CLUSTER + 1):
         plan = plan_model(grid, space_order, nbl, cmin)
         if plan is None or plan.cluster in seen:
             continue
@@ -80,7 +81,7 @@ def partition_shots(grid, space_order, nbl, nshots):
     n <= slots_p else cost_p + best(n - slots_p)."""
     g = grid_struct(grid, space_order)
     cands, seen = [], set()
-    for cmin in range(1, 9):
+    for cmin in range(1, MAX_CLUSTER + 1):
         plan = plan_model(grid, space_order, nbl, cmin)
         if plan is None or plan.cluster in seen:
             continue

@@ -77,6 +77,10 @@ int32_t b2fwi_version(void);
 const char *b2fwi_last_error(void);
 /* Number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t b2fwi_launch_count(void);
+/* Engine switches for A/B runs and the parity tests (process-wide; not thread-safe against running sweeps).
+ *   "tma": bit 0 = TMA-staged forward sweep, bit 1 = TMA-staged adjoint + imaging sweep (default 3; 0 = the
+ *          register-staged kernels everywhere). Returns the previous value (>= 0) or B2FWI_EINVAL. */
+int b2fwi_set_option(const char *name, int32_t value);
 
 /* Layout of one haloed slice: element strides per dimension, offset of domain cell (0,..,0), total floats. */
 int b2fwi_field_layout(const b2fwi_grid *g, int64_t stride_out[3], int64_t *base_out, int64_t *elems_out);
@@ -205,7 +209,7 @@ typedef struct b2fwi_res2d_maps {
 } b2fwi_res2d_maps;
 
 /* Decomposition of a 2-D grid onto clusters; window = the grid minus `nbl` cells on every side.
- * min_cluster: smallest cluster size to try (1..8). Returns B2FWI_EUNSUPPORTED when nothing fits. */
+ * min_cluster: smallest cluster size to try (1..16; sizes above 8 are non-portable cluster sizes, which sm_100 offers). Returns B2FWI_EUNSUPPORTED when nothing fits. */
 int b2fwi_res2d_plan_model(const b2fwi_grid *g, int32_t nbl, int32_t min_cluster, b2fwi_res2d_plan *plan_out);
 
 /* Number of clusters (= shots) of this plan that the current device keeps resident at the same time

@@ -344,3 +344,121 @@ def test_fwi_objective_with_checkpointing_2d():
     assert f0 == f1 and np.array_equal(np.asarray(r0), np.asarray(r1))
     assert np.array_equal(g0, g1) and np.array_equal(i0, i1)
     assert np.abs(g0).max() > 0 and np.abs(i0).max() > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# 3-D shapes whose TMA tiles lie wholly INSIDE the undamped box (stream_tma.cu: `tile_in_box`, the skipped c1 load,
+# the reduced expect_tx byte count and the blo_p..bhi_p plane test). A 128-z tile (so <= 8) needs padded
+# nz >= 256 + nbl, a 64-z tile (so > 8) padded nz >= 128 + nbl; rows 16..48 must sit inside [nbl, ny + nbl).
+def _layered_3d(b, so, shape, nbl, tn, f0=0.02):
+    vp = np.full(shape, 1.5, dtype=np.float32)
+    vp[..., shape[2] // 3:] = 2.2
+    vp[..., 2 * shape[2] // 3:] = 2.9
+    vp[shape[0] // 3: shape[0] // 2, 8:18, shape[2] // 4: shape[2] // 2] = 2.6
+    model = b.Model(origin=(0., 0., 0.), spacing=(10., 10., 10.), shape=shape, space_order=so, vp=vp,
+                    nbl=nbl, bcs="damp")
+    ext = [10. * (n - 1) for n in shape]
+    src = np.array([[0.49 * ext[0], 0.51 * ext[1], 0.31 * ext[2]]])
+    rx, ry = np.meshgrid(np.linspace(12.5, ext[0] - 9.9, 7), np.linspace(8.2, ext[1] - 8.1, 6), indexing='ij')
+    # receivers on a tilted plane through the volume so that residual injection hits in-box tiles as well
+    rz = np.linspace(0.12 * ext[2], 0.83 * ext[2], rx.size)
+    rec = np.stack([rx.ravel(), ry.ravel(), rz], axis=1)
+    geom = b.AcquisitionGeometry(model, rec, src, 0., tn, f0=f0, src_type='Ricker')
+    return model, geom, src, rec
+
+
+@pytest.mark.parametrize("so,shape,nbl", [(8, (24, 40, 300), 9), (16, (24, 40, 160), 9), (4, (26, 36, 290), 9),
+                                          (8, (30, 24, 220), 40)])
+def test_forward_gradient_3d_tiles_inside_undamped_box(so, shape, nbl):
+    """Traces, wavefield and gradient vs the fp64 oracle on shapes where whole TMA tiles skip the c1 load;
+    and the TMA kernels vs the register-staged kernels (B2FWI_TMA=0) on the same inputs."""
+    b = _b()
+    model, geom, src, rec = _layered_3d(b, so, shape, nbl, tn=110.)
+    NZ, NY = model.grid.shape[2], model.grid.shape[1]
+    tz = 128 if so <= 8 else 64
+    # the premise of this test: at least one whole (tz x 16) tile inside [nbl, N - nbl) in z and rows
+    assert any(z0 >= nbl and z0 + tz <= NZ - nbl for z0 in range(0, NZ, tz))
+    assert any(r0 >= nbl and r0 + 16 <= NY - nbl for r0 in range(0, NY, 16))
+    solver = b.AcousticWaveSolver(model, geom, space_order=so)
+    d, u, _ = solver.forward(save=True)
+    rm = ref_model(model)
+    nt, dt = geom.nt, float(geom.dt)
+    d64, u64 = ref.forward(rm, src, rec, np.float64(geom.src.data), nt, dt, save=True, space_order=so)
+    e, eu = rel_l2(d.data, d64), rel_l2(u.data, u64)
+    residual = b.Receiver(name='res', grid=model.grid, time_range=geom.time_axis, coordinates=rec)
+    residual.data[:] = d64
+    grad, _ = solver.gradient(rec=residual, u=u)
+    g64 = ref.gradient(rm, d64, rec, u64, nt, dt, space_order=so)
+    eg = rel_l2(grad.data, g64)
+    del u64
+    print("3-D in-box so=%d %s nbl=%d (padded %s, nt=%d): traces %.2e wavefield %.2e gradient %.2e"
+          % (so, shape, nbl, model.grid.shape, nt, e, eu, eg))
+    assert e <= TOL_TRACE and eu <= TOL_TRACE and eg <= TOL_GRAD
+    # checkpointed gradient (u.dt2 imaging kernel, IMG = 2) == saved-history gradient, bit for bit
+    grad_c, _ = solver.gradient(rec=residual, u=None, checkpointing=True, segment=9)
+    assert np.array_equal(grad_c.data, grad.data)
+    # same sweeps on the register-staged kernels (no TMA, c1 always loaded): shared point_update() => bitwise equal
+    from devito_fwi_b200 import _lib
+    old = _lib.lib().b2fwi_set_option(b"tma", 0)
+    assert old == 3
+    try:
+        solver2 = b.AcousticWaveSolver(model, geom, space_order=so)
+        d2, u2, _ = solver2.forward(save=True)
+        grad2, _ = solver2.gradient(rec=residual, u=u2)
+    finally:
+        _lib.lib().b2fwi_set_option(b"tma", old)
+    assert np.array_equal(d2.data, d.data)
+    assert np.array_equal(u2.data[nt - 1], u.data[nt - 1])
+    assert np.array_equal(grad2.data, grad.data)
+
+
+def test_592_cubed_sweeps_vs_fp32_oracle():
+    """BASELINE configs[4] at full size (592^3 padded, so=8, nbl=40): a few forward and adjoint+imaging steps from a
+    random full-volume initial state (every tile, every plane chunk and the in-box c1 skip carry signal) against the
+    fp32 CPU oracle. Needs ~25 GB of host memory."""
+    import psutil
+    if psutil.virtual_memory().available < 40e9:
+        pytest.skip("needs 40 GB of free host memory")
+    b = _b()
+    from devito_fwi_b200 import configs
+    geom = configs.layered3d(n=512, space_order=8, tn=12.0, rec_decimate=16)
+    model = geom.model
+    nt, dt = geom.nt, float(geom.dt)
+    assert model.grid.shape == (592, 592, 592) and nt >= 6
+    rng = np.random.default_rng(5)
+    from scipy.ndimage import uniform_filter
+
+    def smooth_field():
+        f = rng.standard_normal(model.grid.shape, dtype=np.float32)
+        return uniform_filter(f, 3, mode='constant')
+
+    u = b.TimeFunction(name='u', grid=model.grid, time_order=2, space_order=8, save=nt)
+    u0, u1 = smooth_field(), smooth_field()
+    u.data[0] = u0
+    u.data[1] = u1
+    solver = b.AcousticWaveSolver(model, geom, space_order=8)
+    d, u, _ = solver.forward(save=True, u=u)
+    rm = ref_model(model, dtype=np.float32)
+    uo = np.zeros((nt,) + model.grid.shape, dtype=np.float32)
+    uo[0], uo[1] = u0, u1
+    wav = np.asarray(geom.src.data, dtype=np.float32)
+    do, uo = ref.forward(rm, geom.src_positions, geom.rec_positions, wav, nt, dt, save=True, u=uo, space_order=8)
+    e = rel_l2(d.data[1:nt - 1], do[1:nt - 1])
+    eu = max(rel_l2(u.data[t], uo[t]) for t in (2, nt - 1))
+    print("592^3 forward (%d steps): traces %.2e wavefield %.2e" % (nt - 2, e, eu))
+    assert e <= TOL_TRACE and eu <= TOL_TRACE
+    # adjoint + imaging from a random adjoint state, residual = recorded data
+    v = b.TimeFunction(name='v', grid=model.grid, time_order=2, space_order=8)
+    v0, v1 = smooth_field(), smooth_field()
+    v.data[(nt - 2) % 3] = v0
+    v.data[(nt - 1) % 3] = v1
+    res = b.Receiver(name='res', grid=model.grid, time_range=geom.time_axis, coordinates=geom.rec_positions)
+    res.data[:] = do
+    grad, _ = solver.gradient(rec=res, u=u, v=v)
+    vo = np.zeros((3,) + model.grid.shape, dtype=np.float32)
+    vo[(nt - 2) % 3], vo[(nt - 1) % 3] = v0, v1
+    go = ref.gradient(rm, do, geom.rec_positions, uo, nt, dt, v=vo, space_order=8)
+    eg = rel_l2(grad.data, go)
+    ev = rel_l2(v.data[0 % 3], vo[0 % 3])
+    print("592^3 adjoint+imaging: gradient %.2e adjoint field %.2e" % (eg, ev))
+    assert eg <= TOL_GRAD and ev <= TOL_TRACE
