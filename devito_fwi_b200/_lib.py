@@ -11,7 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libb2fwi.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "stream_kernels.cu", "stream_tma.cu", "resident2d.cu", "res2d_api.cu"]
+SOURCES = ["api.cu", "stream_kernels.cu", "stream_tma.cu", "resident2d.cu", "resident2d_lat.cu", "resident2d_lat_r2.cu",
+           "resident2d_lat_r3.cu", "resident2d_lat_r4.cu", "res2d_api.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(_ROOT, "include")]
@@ -104,7 +105,8 @@ PROTOTYPES = {
     "b2fwi_born": (ctypes.c_int, [_G, _P, _P, _F, _I, _I, _I, _P, _S, _P, _S, _P, _P, _P, _P, _P]),
     "b2fwi_geometry_mask": (ctypes.c_int, [_G, _I, _P, _I, _P, _P]),
     "b2fwi_crop_mask_accumulate": (ctypes.c_int, [_G, _I, _P, _P, _P, _P]),
-    "b2fwi_res2d_plan_model": (ctypes.c_int, [_G, _I, _I, _P]),
+    "b2fwi_res2d_plan_model": (ctypes.c_int, [_G, _I, _I, _I, _P]),
+    "b2fwi_res2d_plan_exact": (ctypes.c_int, [_G, _I, _I, _I, _P]),
     "b2fwi_res2d_max_active_clusters": (ctypes.c_int, [_G, _P, _P]),
     "b2fwi_res2d_prepare": (ctypes.c_int, [_G, _P, _F, _P, _P]),
     "b2fwi_res2d_forward": (ctypes.c_int, [_G, _P, _P, _P, _P, _F, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P]),

@@ -14,7 +14,7 @@ int res2d_max_clusters(const Res2dArgs &a, int R, int P, int *out);
 
 static const int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
 
-static int max_threads_for(int P) { return P <= 4 ? 512 : P <= 8 ? 480 : P <= 12 ? 384 : 288; }
+static int max_threads_for(int P) { return P <= RES2D_LAT_MAXP ? 512 : P <= 8 ? 480 : P <= 12 ? 384 : 288; }
 static const int kMaxCluster = 16;     // 9..16 = non-portable cluster sizes (cudaFuncAttributeNonPortableClusterSizeAllowed)
 
 __global__ void bcoef_kernel(const float *__restrict__ vp, double dt, float *__restrict__ B, int64_t n)
@@ -252,6 +252,8 @@ static int fill_args(const b2fwi_grid *g, const b2fwi_res2d_plan *p, Res2dArgs *
     B2_CHECK_ARG(a->wx0 >= 0 && a->wx1 <= a->nx && a->wx0 < a->wx1 && a->wq0 >= 0 && a->wq1 <= a->nzq && a->wq0 < a->wq1,
                  "bad window");
     B2_CHECK_ARG((int)res2d_smem_bytes(*a, p->rows_per_thread) <= kMaxSmem, "plan exceeds shared memory");
+    B2_CHECK_ARG(p->tile_pitch == (p->rows_per_thread <= RES2D_LAT_MAXP ? 4 * res2d_lat_pitch_quads(a->nzq) : 4 * (a->nzq + 2)),
+                 "tile pitch %d does not match the kernel's", p->tile_pitch);
     return 0;
 }
 
@@ -268,45 +270,72 @@ using namespace b2fwi;
 
 extern "C" {
 
-int b2fwi_res2d_plan_model(const b2fwi_grid *g, int32_t nbl, int32_t min_cluster, b2fwi_res2d_plan *out)
+// plan for exactly (C CTAs per shot, P rows per thread); B2FWI_EUNSUPPORTED when it does not fit
+static int plan_exact(const b2fwi_grid *g, const Layout &L, int nbl, int C, int P, b2fwi_res2d_plan *out)
 {
-    Layout L;
-    int rc = make_layout(g, &L);
+    const int nx = g->shape[0], nz = g->shape[1], nzq = (nz + 3) / 4;
+    const bool lat = P <= RES2D_LAT_MAXP;
+    if (C < 1 || C > kMaxCluster || !(P == 3 || P == 4 || P == 8 || P == 12 || P == 16)) return B2FWI_EUNSUPPORTED;
+    const int rows_cta = (nx + C - 1) / C;
+    if (rows_cta * (C - 1) >= nx) return B2FWI_EUNSUPPORTED;
+    if (nx - rows_cta * (C - 1) < L.R || rows_cta < 2 * L.R) return B2FWI_EUNSUPPORTED;
+    if (lat && res2d_lat_pitch_quads(nzq) == 0) return B2FWI_EUNSUPPORTED;
+    const int G = (rows_cta + P - 1) / P;
+    const int threads = (nzq * G + 31) / 32 * 32;
+    if (threads > max_threads_for(P)) return B2FWI_EUNSUPPORTED;
+    Res2dArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nzq = nzq; a.rows_cta = rows_cta; a.G = G; a.tile_rows = G * P + 2 * L.R;
+    a.wq0 = nbl / 4; a.wq1 = (nz - nbl + 3) / 4;
+    const size_t smem = res2d_smem_bytes(a, P);
+    if (smem > (size_t)kMaxSmem) return B2FWI_EUNSUPPORTED;
+    out->cluster = C; out->rows_per_thread = P; out->groups = G; out->threads = threads;
+    out->rows_cta = rows_cta; out->tile_rows = a.tile_rows; out->smem_bytes = (int32_t)smem;
+    out->wx0 = nbl; out->wx1 = nx - nbl; out->wq0 = a.wq0; out->wq1 = a.wq1;
+    out->tile_pitch = lat ? 4 * res2d_lat_pitch_quads(nzq) : 4 * (nzq + 2);
+    return 0;
+}
+
+static int plan_prologue(const b2fwi_grid *g, int32_t nbl, b2fwi_res2d_plan *out, Layout *L)
+{
+    int rc = make_layout(g, L);
     if (rc) return rc;
     B2_CHECK_ARG(out != nullptr, "plan_out is NULL");
-    if (g->ndim != 2 || L.R < 2 || L.R > 4 || g->halo != 0) {
+    if (g->ndim != 2 || L->R < 2 || L->R > 4 || g->halo != 0) {
         set_error("resident engine: needs a 2-D grid, halo 0 and space_order 4, 6 or 8");
         return B2FWI_EUNSUPPORTED;
     }
-    const int nx = g->shape[0], nz = g->shape[1], nzq = (nz + 3) / 4;
-    B2_CHECK_ARG(nbl >= 0 && 2 * nbl < nx && 2 * nbl < nz, "bad nbl %d", nbl);
+    B2_CHECK_ARG(nbl >= 0 && 2 * nbl < g->shape[0] && 2 * nbl < g->shape[1], "bad nbl %d", nbl);
+    return 0;
+}
+
+int b2fwi_res2d_plan_model(const b2fwi_grid *g, int32_t nbl, int32_t min_cluster, int32_t min_rows_per_thread,
+                           b2fwi_res2d_plan *out)
+{
+    Layout L;
+    int rc = plan_prologue(g, nbl, out, &L);
+    if (rc) return rc;
     if (min_cluster < 1) min_cluster = 1;
-    // rows per thread: the smallest strip whose thread count fits (more warps per SM hide the dependent chain of a
-    // row better; longer strips only amortise the 2R-row window fill)
+    // rows per thread: the shortest strip whose thread count fits (time per step goes with warps per scheduler x
+    // rows per thread; longer strips only amortise the 2R-row window fill)
     const int Ps[4] = {4, 8, 12, 16};
-    for (int C = min_cluster; C <= kMaxCluster; C++) {
-        const int rows_cta = (nx + C - 1) / C;
-        if (rows_cta * (C - 1) >= nx) continue;
-        if (nx - rows_cta * (C - 1) < L.R || rows_cta < 2 * L.R) continue;
-        for (int ip = 0; ip < 4; ip++) {
-            const int P = Ps[ip];
-            const int G = (rows_cta + P - 1) / P;
-            const int threads = (nzq * G + 31) / 32 * 32;
-            if (threads > max_threads_for(P)) continue;
-            Res2dArgs a;
-            memset(&a, 0, sizeof(a));
-            a.nzq = nzq; a.rows_cta = rows_cta; a.G = G; a.tile_rows = G * P + 2 * L.R;
-            a.wq0 = nbl / 4; a.wq1 = (nz - nbl + 3) / 4;
-            const size_t smem = res2d_smem_bytes(a, P);
-            if (smem > (size_t)kMaxSmem) continue;
-            out->cluster = C; out->rows_per_thread = P; out->groups = G; out->threads = threads;
-            out->rows_cta = rows_cta; out->tile_rows = a.tile_rows; out->smem_bytes = (int32_t)smem;
-            out->wx0 = nbl; out->wx1 = nx - nbl; out->wq0 = a.wq0; out->wq1 = a.wq1;
-            return 0;
-        }
-    }
-    set_error("resident engine: grid %dx%d (space_order %d) does not fit a cluster of <= 16 SMs", nx, nz, g->space_order);
+    for (int C = min_cluster; C <= kMaxCluster; C++)
+        for (int ip = 0; ip < 4; ip++)
+            if (Ps[ip] >= min_rows_per_thread && plan_exact(g, L, nbl, C, Ps[ip], out) == 0) return 0;
+    set_error("resident engine: grid %dx%d (space_order %d) does not fit a cluster of <= 16 SMs", g->shape[0], g->shape[1],
+              g->space_order);
     return B2FWI_EUNSUPPORTED;
+}
+
+int b2fwi_res2d_plan_exact(const b2fwi_grid *g, int32_t nbl, int32_t cluster, int32_t rows_per_thread,
+                           b2fwi_res2d_plan *out)
+{
+    Layout L;
+    int rc = plan_prologue(g, nbl, out, &L);
+    if (rc) return rc;
+    rc = plan_exact(g, L, nbl, cluster, rows_per_thread, out);
+    if (rc) set_error("resident engine: no plan with %d CTAs per shot and %d rows per thread", cluster, rows_per_thread);
+    return rc;
 }
 
 int b2fwi_res2d_max_active_clusters(const b2fwi_grid *g, const b2fwi_res2d_plan *plan, int32_t *out)

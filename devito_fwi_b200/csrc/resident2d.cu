@@ -117,7 +117,7 @@ template <typename T>
 static __device__ __forceinline__ void opaque_ptr(T *&p) { asm volatile("" : "+l"(p)); }
 
 template <int P>
-struct MaxThreads { static constexpr int value = (P <= 4) ? 512 : (P <= 8) ? 480 : (P <= 12) ? 384 : 288; };
+struct MaxThreads { static constexpr int value = (P <= 8) ? 480 : (P <= 12) ? 384 : 288; };
 
 // MODE 0: forward (record receivers, store u.dt2 history, accumulate illumination)
 // MODE 1: backward with imaging condition (read u.dt2 history, accumulate gradient)
@@ -493,6 +493,7 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
 // ------------------------------------------------------------------------------------------------
 size_t res2d_smem_bytes(const Res2dArgs &a, int P)
 {
+    if (P <= RES2D_LAT_MAXP) return res2d_lat_smem_bytes(a);
     const size_t pitch = ((size_t)a.nzq + 2) * 4;
     const size_t wcols = (size_t)(a.wq1 - a.wq0) * 4;
     return sizeof(float) * (2 * (size_t)a.tile_rows * pitch + (size_t)a.rows_cta * wcols + (size_t)a.G * P +
@@ -529,7 +530,6 @@ template <int R, int MODE>
 static int launch_P(const Res2dArgs &a, int P, cudaStream_t st)
 {
     switch (P) {
-    case 4: return launch_one<R, 4, MODE>(a, st);
     case 8: return launch_one<R, 8, MODE>(a, st);
     case 12: return launch_one<R, 12, MODE>(a, st);
     case 16: return launch_one<R, 16, MODE>(a, st);
@@ -564,8 +564,9 @@ static int max_clusters_one(const Res2dArgs &a, int *out)
 int res2d_max_clusters(const Res2dArgs &a, int R, int P, int *out)
 {
 #define B2_OCASE(r, p) if (R == r && P == p) return max_clusters_one<r, p>(a, out);
-    B2_OCASE(2, 4) B2_OCASE(2, 8) B2_OCASE(2, 12) B2_OCASE(2, 16) B2_OCASE(3, 4) B2_OCASE(3, 8) B2_OCASE(3, 12)
-    B2_OCASE(3, 16) B2_OCASE(4, 4) B2_OCASE(4, 8) B2_OCASE(4, 12) B2_OCASE(4, 16)
+    if (P <= RES2D_LAT_MAXP) return res2d_lat_max_clusters(a, R, P, out);
+    B2_OCASE(2, 8) B2_OCASE(2, 12) B2_OCASE(2, 16) B2_OCASE(3, 8) B2_OCASE(3, 12) B2_OCASE(3, 16)
+    B2_OCASE(4, 8) B2_OCASE(4, 12) B2_OCASE(4, 16)
 #undef B2_OCASE
     set_error("res2d: unsupported (R, P) = (%d, %d)", R, P);
     return B2FWI_EUNSUPPORTED;
@@ -573,6 +574,7 @@ int res2d_max_clusters(const Res2dArgs &a, int R, int P, int *out)
 
 int launch_res2d(const Res2dArgs &a, int R, int P, int mode, cudaStream_t st)
 {
+    if (P <= RES2D_LAT_MAXP) return launch_res2d_lat(a, R, P, mode, st);
     if (a.threads > (P <= 4 ? 512 : P <= 8 ? 480 : P <= 12 ? 384 : 288)) {
         set_error("res2d: %d threads exceed the limit for P=%d", a.threads, P);
         return B2FWI_EINVAL;

@@ -6,6 +6,9 @@ namespace b2fwi {
 
 #define RES2D_MAX_CELLS 1024   // injection cells per CTA (shared-memory staging, double buffered)
 #define RES2D_MAX_CON 1024     // injection contributions (point, weight) per CTA, staged in shared memory
+// 4-row-strip variant (resident2d_lat.cu): staged source / residual row (points used by one CTA) and receiver tables
+#define RES2D_LAT_MAXV 1024
+#define RES2D_LAT_MAXITP 1024
 
 struct Res2dArgs {
     // ---- decomposition (b2fwi_res2d_plan)
@@ -53,5 +56,12 @@ struct Res2dArgs {
     // ---- window accumulator written at the end: illumination (forward) or gradient (backward)
     float *out;                 // [shot][wx1-wx0][(wq1-wq0)*4]
 };
+
+// short strips (3 or 4 rows per thread), few shots per GPU (resident2d_lat.cu)
+#define RES2D_LAT_MAXP 4
+int launch_res2d_lat(const Res2dArgs &a, int R, int P, int mode, cudaStream_t st);
+int res2d_lat_pitch_quads(int nzq);      // tile row pitch of the short-strip kernels (0: rows too long for them)
+size_t res2d_lat_smem_bytes(const Res2dArgs &a);
+int res2d_lat_max_clusters(const Res2dArgs &a, int R, int P, int *out);
 
 }  // namespace b2fwi

@@ -1,0 +1,9 @@
+// resident2d_lat_r2.cu -- instantiates the short-strip resident kernels (resident2d_lat.cuh) for space_order 4
+#include "resident2d_lat.cuh"
+
+namespace b2fwi {
+int lat_dispatch_r2(const Res2dArgs &a, int P, int mode, int op, cudaStream_t st, int *out)
+{
+    return lat_dispatch<2>(a, P, mode, op, st, out);
+}
+}  // namespace b2fwi

@@ -252,9 +252,8 @@ def _resident_surveys(geometry, shots):
             return None
         try:
             svs, k0 = [], 0
-            for count, cluster in groups:
-                svs.append(ResidentSurvey(geometry, shots[k0:k0 + count],
-                                          min_cluster=cluster if len(groups) > 1 else 1))
+            for count, plan in groups:
+                svs.append(ResidentSurvey(geometry, shots[k0:k0 + count], plan=plan))
                 k0 += count
         except ValueError:
             return None

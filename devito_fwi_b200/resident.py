@@ -21,13 +21,15 @@ __all__ = ['ResidentSurvey', 'plan_model']
 MAX_CELLS = 1024      # RES2D_MAX_CELLS
 MAX_CON = 1024        # RES2D_MAX_CON (contributions per CTA; point indices are staged as uint16)
 MAX_CLUSTER = 16      # CTAs (SMs) per shot; 9..16 are non-portable cluster sizes
+LAT_MAXV = 1024       # RES2D_LAT_MAXV / RES2D_LAT_MAXITP: staging limits of the 4-row-strip kernel (resident2d_lat.cu)
+LAT_MAXITP = 1024
 
 
 class Plan(ctypes.Structure):
     """struct b2fwi_res2d_plan"""
     _fields_ = [(n, ctypes.c_int32) for n in
                 ('cluster', 'rows_per_thread', 'groups', 'threads', 'rows_cta', 'tile_rows', 'smem_bytes',
-                 'wx0', 'wx1', 'wq0', 'wq1')]
+                 'wx0', 'wx1', 'wq0', 'wq1', 'tile_pitch')]
 
 
 class Maps(ctypes.Structure):
@@ -37,60 +39,90 @@ class Maps(ctypes.Structure):
                  'itp_desc', 'itp_pt', 'itp_off', 'itp_w')]
 
 
-def plan_model(grid, space_order, nbl, min_cluster=1):
-    """b2fwi_res2d_plan_model; returns a Plan or None when the grid does not fit the engine."""
+def plan_model(grid, space_order, nbl, min_cluster=1, min_rows=1):
+    """b2fwi_res2d_plan_model (first fit from `min_cluster` upwards); a Plan, or None when the grid does not fit."""
     if grid.dim != 2 or space_order not in (4, 6, 8):
         return None
     g = grid_struct(grid, space_order)
     plan = Plan()
-    rc = _lib.lib().b2fwi_res2d_plan_model(ctypes.byref(g), int(nbl), int(min_cluster), ctypes.byref(plan))
+    rc = _lib.lib().b2fwi_res2d_plan_model(ctypes.byref(g), int(nbl), int(min_cluster), int(min_rows),
+                                           ctypes.byref(plan))
     return plan if rc == 0 else None
 
 
-def choose_plan(grid, space_order, nbl, nshots):
-    """Cluster size for `nshots` concurrent shots: among the feasible decompositions pick the one that
-    minimises (waves of resident clusters) x (rows per CTA) -- few shots get more SMs each, many shots the
-    smallest cluster that fits. Uses cudaOccupancyMaxActiveClusters through the C ABI."""
+def plan_exact(grid, space_order, nbl, cluster, rows):
+    """b2fwi_res2d_plan_exact: the plan with `cluster` CTAs per shot and `rows` rows per thread, or None."""
+    if grid.dim != 2 or space_order not in (4, 6, 8):
+        return None
     g = grid_struct(grid, space_order)
-    best, best_cost, seen = None, None, set()
-    for cmin in range(1, MAX_CLUSTER + 1):
-        plan = plan_model(grid, space_order, nbl, cmin)
-        if plan is None or plan.cluster in seen:
-            continue
-        seen.add(plan.cluster)
-        n = ctypes.c_int32()
-        rc = _lib.lib().b2fwi_res2d_max_active_clusters(ctypes.byref(g), ctypes.byref(plan), ctypes.byref(n))
-        if rc != 0 or n.value <= 0:
-            continue
-        waves = -(-nshots // n.value)
-        cost = waves * plan.rows_cta * (1.0 + 0.02 * plan.cluster)       # mild penalty: wider barrier
+    plan = Plan()
+    rc = _lib.lib().b2fwi_res2d_plan_exact(ctypes.byref(g), int(nbl), int(cluster), int(rows), ctypes.byref(plan))
+    return plan if rc == 0 else None
+
+
+ROWS_PER_THREAD = (3, 4, 8, 12, 16)
+
+
+def step_cost(plan):
+    """Relative time of one time step of a cluster with this plan (fitted to B200 measurements, Marmousi / circle /
+    Marmousi2, 1-29 shots, profiles/r02_res2d_plans.txt): a step is paced by the busiest of the 4 warp schedulers of an
+    SM, i.e. by (warps per scheduler) x (rows per thread + window fill), plus a fixed part per step -- small for the
+    short-strip kernels (everything per-point lives in registers / shared memory), large for the long-strip kernel
+    (B and the history are re-read from L2 every row)."""
+    wps = -(-(plan.threads // 32) // 4)
+    P = plan.rows_per_thread
+    if P <= 4:
+        c = 0.56 + 0.227 * wps * (P + 2)
+        return c * (1.1 if plan.threads > 384 else 1.0)       # 4 warps per scheduler: 128 registers, batches of 2 rows
+    return 4.9 + 0.263 * max(wps, 3) * P * (1.35 if P >= 16 else 1.0)     # 16-row strips spill
+
+
+def candidates(grid, space_order, nbl, min_rows=1):
+    """Every feasible decomposition as (plan, clusters the device keeps resident)."""
+    g = grid_struct(grid, space_order)
+    out = []
+    for C in range(1, MAX_CLUSTER + 1):
+        for P in ROWS_PER_THREAD:
+            if P < min_rows:
+                continue
+            plan = plan_exact(grid, space_order, nbl, C, P)
+            if plan is None:
+                continue
+            n = ctypes.c_int32()
+            rc = _lib.lib().b2fwi_res2d_max_active_clusters(ctypes.byref(g), ctypes.byref(plan), ctypes.byref(n))
+            if rc == 0 and n.value > 0:
+                out.append((plan, int(n.value)))
+    return out
+
+
+_CANDS = {}
+
+
+def _cands(grid, space_order, nbl, min_rows):
+    key = (grid._key(), space_order, nbl, min_rows)
+    if key not in _CANDS:
+        _CANDS[key] = candidates(grid, space_order, nbl, min_rows)
+    return _CANDS[key]
+
+
+def choose_plan(grid, space_order, nbl, nshots, min_rows=1):
+    """Decomposition for `nshots` concurrent shots in ONE launch: minimises (waves of resident clusters) x (time per
+    step) -- few shots get up to 16 SMs each and short strips, many shots the smallest cluster that fits."""
+    best, best_cost = None, None
+    for plan, slots in _cands(grid, space_order, nbl, min_rows):
+        cost = -(-nshots // slots) * step_cost(plan)
         if best is None or cost < best_cost:
             best, best_cost = plan, cost
     return best
 
 
-def partition_shots(grid, space_order, nbl, nshots):
-    """Split ``nshots`` concurrent shots into launch groups [(count, min_cluster), ...].
+def partition_shots(grid, space_order, nbl, nshots, min_rows=1):
+    """Split ``nshots`` concurrent shots into launch groups [(count, plan), ...].
 
-    One launch keeps ``slots`` clusters resident; more shots than that run in waves, and the last wave is
-    usually far from full. Cheaper: give each wave its own launch and its own decomposition - a full wave of
-    the smallest cluster, then the remainder on wider clusters (fewer rows per CTA = faster steps). The cost of
-    a group is one wave = rows per CTA (x a mild penalty for wider barriers) + a fixed part (per-step barrier and
-    dependency latency do not shrink with the strip: measured on Marmousi2, 70 -> 53 rows per CTA takes a wave
-    from 20 to 17.5 ms, i.e. the fixed part is worth ~60 rows); best(n) = min over plans p of cost_p if
-    n <= slots_p else cost_p + best(n - slots_p)."""
-    g = grid_struct(grid, space_order)
-    cands, seen = [], set()
-    for cmin in range(1, MAX_CLUSTER + 1):
-        plan = plan_model(grid, space_order, nbl, cmin)
-        if plan is None or plan.cluster in seen:
-            continue
-        seen.add(plan.cluster)
-        n = ctypes.c_int32()
-        rc = _lib.lib().b2fwi_res2d_max_active_clusters(ctypes.byref(g), ctypes.byref(plan), ctypes.byref(n))
-        if rc != 0 or n.value <= 0:
-            continue
-        cands.append((plan.rows_cta * (1.0 + 0.02 * plan.cluster) + 60.0, int(n.value), int(plan.cluster)))
+    One launch keeps ``slots`` clusters resident; more shots than that run in waves, and the last wave is usually far
+    from full. Cheaper: give each wave its own launch and its own decomposition - a full wave of the smallest cluster,
+    then the remainder on wider clusters with shorter strips; best(n) = min over plans p of cost_p + best(n - slots_p)."""
+    cands = [(step_cost(plan), slots, plan) for plan, slots in _cands(grid, space_order, nbl, min_rows)]
     return best_partition(cands, nshots)
 
 
@@ -127,7 +159,7 @@ def build_maps(grid, plan, R, inj_coords, itp_coords=None):
     rows_cta = plan.rows_cta
     nzq = (grid.shape[1] + 3) // 4
     gpitch = grid.pitch
-    spitch = (nzq + 2) * 4            # shared tile row pitch: one zero quad on each side (resident2d.cu)
+    spitch = plan.tile_pitch          # shared tile row pitch; one zero quad on each side of a row (resident2d.cu)
     nshots = len(inj_coords)
     inj_desc = np.zeros((nshots * C, 2), dtype=np.int32)
     thr_mask = np.zeros((nshots * C, T), dtype=np.uint64)
@@ -158,6 +190,8 @@ def build_maps(grid, plan, R, inj_coords, itp_coords=None):
             ncell = cells.size
             if ncell > MAX_CELLS or k.size > MAX_CON or npoint > 65535:
                 return None
+            if P <= 4 and k.size and int(v_pt[sel].max()) - int(v_pt[sel].min()) + 1 > LAT_MAXV:
+                return None         # the short-strip kernels stage the span of points one CTA uses
             inj_desc[sc] = (ncell, cell_base)
             cptr = np.concatenate([start, [k.size]]).astype(np.int32) + ncontrib
             cptr_all.append(cptr)
@@ -196,6 +230,8 @@ def build_maps(grid, plan, R, inj_coords, itp_coords=None):
             owner = np.clip(ix, 0, nx - 1) // rows_cta
             for c in range(C):
                 sel = np.nonzero(owner == c)[0]
+                if P <= 4 and sel.size > LAT_MAXITP:
+                    return None
                 sc = s * C + c
                 itp_desc[sc] = (sel.size, base)
                 trow = row[sel] - c * rows_cta + R
@@ -227,7 +263,7 @@ class _DevMaps(object):
 class ResidentSurvey(object):
     """Device-resident state of the shots ``shots`` of ``geometry`` (default: all of them)."""
 
-    def __init__(self, geometry, shots=None, space_order=None, min_cluster=1):
+    def __init__(self, geometry, shots=None, space_order=None, min_cluster=1, min_rows=1, plan=None):
         import torch
         self.geometry = geometry
         model = self.model = geometry.model
@@ -236,8 +272,11 @@ class ResidentSurvey(object):
         self.R = self.space_order // 2
         self.shots = list(range(geometry.nsrc)) if shots is None else list(shots)
         self.nshots = len(self.shots)
-        self.plan = (choose_plan(self.grid, self.space_order, model.nbl, self.nshots) if min_cluster == 1
-                     else plan_model(self.grid, self.space_order, model.nbl, min_cluster))
+        if plan is not None:
+            self.plan = plan
+        else:
+            self.plan = (choose_plan(self.grid, self.space_order, model.nbl, self.nshots, min_rows) if min_cluster == 1
+                         else plan_model(self.grid, self.space_order, model.nbl, min_cluster, min_rows))
         if self.plan is None or not self.supported(geometry, self.space_order):
             raise ValueError("model does not fit the SM-resident engine")
         self.nt = geometry.nt
@@ -262,6 +301,10 @@ class ResidentSurvey(object):
         rec_pos = [geometry.rec_positions] * self.nshots
         mf = build_maps(self.grid, p, self.R, src_pos, rec_pos)
         mb = build_maps(self.grid, p, self.R, rec_pos, None)
+        if (mf is None or mb is None) and p.rows_per_thread <= 4 and min_rows < 8:
+            # beyond the staging limits of the short-strip kernels: plan again with longer strips
+            self.__init__(geometry, shots, space_order, min_cluster, min_rows=8)
+            return
         if mf is None or mb is None:
             raise ValueError("too many injection cells per CTA for the SM-resident engine")
         self.maps_fwd, self.maps_bwd = _DevMaps(mf), _DevMaps(mb)

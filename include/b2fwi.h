@@ -192,6 +192,7 @@ typedef struct b2fwi_res2d_plan {
     int32_t smem_bytes;
     int32_t wx0, wx1;         /* window rows, padded-grid coordinates */
     int32_t wq0, wq1;         /* window columns in units of 4 cells (quads) */
+    int32_t tile_pitch;       /* floats per row of the CTA's shared-memory tile (b2fwi_res2d_maps.itp_off is built on it) */
 } b2fwi_res2d_plan;
 
 /* Host-built maps (devito_fwi_b200.resident), indexed by shot*cluster + rank; device pointers. */
@@ -209,8 +210,16 @@ typedef struct b2fwi_res2d_maps {
 } b2fwi_res2d_maps;
 
 /* Decomposition of a 2-D grid onto clusters; window = the grid minus `nbl` cells on every side.
- * min_cluster: smallest cluster size to try (1..16; sizes above 8 are non-portable cluster sizes, which sm_100 offers). Returns B2FWI_EUNSUPPORTED when nothing fits. */
-int b2fwi_res2d_plan_model(const b2fwi_grid *g, int32_t nbl, int32_t min_cluster, b2fwi_res2d_plan *plan_out);
+ * min_cluster: smallest cluster size to try (1..16; sizes above 8 are non-portable cluster sizes, which sm_100
+ * offers). Returns B2FWI_EUNSUPPORTED when nothing fits.
+ * Strips of 3 or 4 rows per thread run the few-shots kernels (resident2d_lat.cuh), which stage at most 1024 receivers per CTA
+ * and a source / residual row span of at most 1024 points per CTA; min_rows_per_thread = 8 plans around it. */
+int b2fwi_res2d_plan_model(const b2fwi_grid *g, int32_t nbl, int32_t min_cluster, int32_t min_rows_per_thread,
+                           b2fwi_res2d_plan *plan_out);
+/* The plan with exactly `cluster` CTAs per shot and `rows_per_thread` in {3, 4, 8, 12, 16}, or B2FWI_EUNSUPPORTED:
+ * the host enumerates these and picks by its cost model (devito_fwi_b200/resident.py). */
+int b2fwi_res2d_plan_exact(const b2fwi_grid *g, int32_t nbl, int32_t cluster, int32_t rows_per_thread,
+                           b2fwi_res2d_plan *plan_out);
 
 /* Number of clusters (= shots) of this plan that the current device keeps resident at the same time
  * (cudaOccupancyMaxActiveClusters); used to pick the cluster size for a given number of shots. */

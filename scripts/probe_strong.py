@@ -11,6 +11,7 @@ from devito_fwi_b200.wavesolver import grid_struct
 torch.zeros(1, device='cuda')
 which = sys.argv[1] if len(sys.argv) > 1 else 'marmousi'
 shot_counts = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [1, 4, 8, 29]
+only_c = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else None
 geom = {'marmousi': lambda: configs.marmousi()[1], 'marmousi2': lambda: configs.marmousi2()[1],
         'circle': lambda: configs.circle()[1]}[which]()
 m = geom.model
@@ -19,9 +20,11 @@ ref_rec = {}
 rows = []
 for ns in shot_counts:
     shots = list(np.linspace(0, geom.nsrc - 1, ns).round().astype(int)) if ns < geom.nsrc else list(range(geom.nsrc))
-    for C in range(1, resident.MAX_CLUSTER + 1):
-        p = resident.plan_model(m.grid, m.space_order, m.nbl, min_cluster=C)
-        if p is None or p.cluster != C:
+    for C, P in [(c, pp) for c in range(1, resident.MAX_CLUSTER + 1) for pp in resident.ROWS_PER_THREAD]:
+        if only_c and C not in only_c:
+            continue
+        p = resident.plan_exact(m.grid, m.space_order, m.nbl, C, P)
+        if p is None:
             continue
         n = ctypes.c_int32()
         rc = _lib.lib().b2fwi_res2d_max_active_clusters(ctypes.byref(g), ctypes.byref(p), ctypes.byref(n))
@@ -31,8 +34,7 @@ for ns in shot_counts:
         if ns > 2 * n.value:
             continue
         try:
-            sv = resident.ResidentSurvey(geom, shots, min_cluster=C)
-            assert sv.plan.cluster == C
+            sv = resident.ResidentSurvey(geom, shots, plan=p)
             rec = sv.forward(save=True, illum=True)
             res = rec.clone()
             sv.gradient(res)
@@ -52,9 +54,9 @@ for ns in shot_counts:
             if key not in ref_rec:
                 ref_rec[key] = (r0, gr)
             same = bool(np.array_equal(ref_rec[key][0], r0) and np.array_equal(ref_rec[key][1], gr))
-            print(which, "ns=%2d C=%2d P=%2d G=%2d T=%3d rows=%3d smem=%6d slots=%2d | fwd %.3f ms adj %.3f ms sum %.3f | per-shot %.3f ms | same=%s"
+            print(which, "ns=%2d C=%2d P=%2d G=%2d T=%3d rows=%3d smem=%6d slots=%2d | fwd %.3f ms adj %.3f ms sum %.3f | per-shot %.3f ms | model %.2f | same=%s"
                   % (ns, C, p.rows_per_thread, p.groups, p.threads, p.rows_cta, p.smem_bytes, n.value, t[0], t[1], t[0] + t[1],
-                     (t[0] + t[1]) / ns, same), flush=True)
+                     (t[0] + t[1]) / ns, resident.step_cost(p) * -(-ns // n.value), same), flush=True)
             rows.append(dict(cfg=which, ns=ns, C=C, P=p.rows_per_thread, T=p.threads, rows=p.rows_cta, slots=n.value,
                              fwd=t[0], adj=t[1]))
             del sv, rec, res

@@ -118,9 +118,10 @@ def test_objective_resident_vs_streaming_vs_oracle():
 
 
 def test_objective_in_launch_groups_matches_single_group(monkeypatch):
-    """Surveys with more shots than one wave of clusters are split into launch groups with their own cluster
-    size (resident.partition_shots). A forced split (3 shots on 4-CTA clusters + 2 shots on 6-CTA clusters)
-    must give the objective, gradient, residuals and fm_multi records of the single-group run."""
+    """Surveys with more shots than one wave of clusters are split into launch groups with their own decomposition
+    (resident.partition_shots). A forced split (3 shots on 4-CTA clusters with 12-row strips = the long-strip
+    kernel, 2 shots on 16-CTA clusters with 3-row strips = the short-strip kernel) must give the objective,
+    gradient, residuals and fm_multi records of the single-group run."""
     from devito_fwi_b200 import configs, fwi, resident
     g_true, g_init, g_const, mask = configs.marmousi(nsrc=5)
     x = (1. / (g_init.model.vp.data[40:-40, 40:-40].astype(np.float64) ** 2)).ravel()
@@ -131,9 +132,12 @@ def test_objective_in_launch_groups_matches_single_group(monkeypatch):
     f1, g1, r1 = fwi.fwi_loss(x, g_init, obs, fwi.least_square, dw, mask, True, True)
     r1 = [np.asarray(r).copy() for r in r1]
     fwi._SURVEYS.clear()
-    monkeypatch.setattr(resident, 'partition_shots', lambda *a, **k: [(3, 4), (2, 6)])
+    grid = g_init.model.grid
+    forced = [(3, resident.plan_exact(grid, 8, 40, 4, 12)), (2, resident.plan_exact(grid, 8, 40, 16, 3))]
+    assert all(p is not None for _, p in forced)
+    monkeypatch.setattr(resident, 'partition_shots', lambda *a, **k: forced)
     svs = fwi._resident_surveys(g_init, list(range(5)))
-    assert [sv.nshots for sv in svs] == [3, 2] and [sv.plan.cluster for sv in svs] == [4, 6]
+    assert [sv.nshots for sv in svs] == [3, 2] and [sv.plan.cluster for sv in svs] == [4, 16]
     assert [sv.shots for sv in svs] == [[0, 1, 2], [3, 4]]
     f2, g2, r2 = fwi.fwi_loss(x, g_init, obs, fwi.least_square, dw, mask, True, True)
     obs2 = fwi.fm_multi(g_true)
