@@ -470,3 +470,68 @@ def fwi_loss(x, geometry, obs, misfit_func, direct_wave=None, mask=None, precond
     v = 1. / np.sqrt(x.reshape(geometry.model.shape))
     geometry.model.update('vp', v.reshape(geometry.model.shape))
     return fwi_obj_multi(geometry, obs, misfit_func, direct_wave, mask, precond, calc_grad)
+
+
+# ---------------------------------------------------------------------------------------------
+class StreamingSurvey(object):
+    """L2 objective and gradient of a multi-shot survey on the STREAMING engine (any model the resident 2-D
+    engine does not take: every 3-D model): the shot loop of fwi.py:183-199 with the per-shot sequence of
+    acoustic_example.py:26-63 -- forward with on-device checkpoints, residual, adjoint + imaging (checkpoint.py)
+    -- shots round-robin over ranks and ONE all-reduce of [grad | fval].
+    No illumination preconditioning / source muting: fix_source_illumination is 2-D only (fwi.py:104-129)."""
+
+    def __init__(self, geometry, keep_segments=None):
+        import torch
+        self.geometry = geometry
+        self.model = geometry.model
+        self.keep_segments = keep_segments
+        grid = self.model.grid
+        self.buf = torch.zeros(grid.slice_elems + 1, dtype=torch.float32, device='cuda')      # [grad | fval]
+        self.grad = Function(name='grad', grid=grid)
+        self.grad._buf._dev = self.buf[:-1].view(grid.slice_shape)       # accumulate straight into the all-reduce buffer
+        self.grad._buf._newer = 'dev'
+        self._host = None
+        self.shots = dist.local_shots(geometry.nsrc)
+        self._geoms = {i: _shot_geometry(geometry, i) for i in self.shots}
+        self._solvers = {i: AcousticWaveSolver(self.model, g, space_order=self.model.space_order, profile=False)
+                         for i, g in self._geoms.items()}
+
+    def forward(self, vp=None):
+        """Synthetic records of this rank's shots (dict shot -> Receiver, data on the device)."""
+        out = {}
+        for i in self.shots:
+            rec = self._solvers[i].forward(vp=vp or self.model.vp)[0]
+            r = Receiver(name='obs', grid=self.model.grid, time_range=self._geoms[i].time_axis,
+                         coordinates=self._geoms[i].rec_positions)
+            r._sdata.adopt_dev(rec._sdata.dev().clone())
+            out[i] = r
+        return out
+
+    def objective(self, obs, host=True):
+        """(fval, grad): sum over all shots and ranks of 0.5*||d_syn - d_obs||^2 and its gradient with respect to
+        the squared slowness on the padded grid. ``obs``: mapping shot -> Receiver. ``host=True`` returns
+        (float, numpy [grid.shape]) through one device-to-host copy; ``host=False`` leaves both in the device
+        buffer and returns (0-d tensor, Function)."""
+        import torch
+        self.buf.zero_()
+        fval = torch.zeros(1, dtype=torch.float64, device='cuda')
+        for i in self.shots:
+            solver, g_i = self._solvers[i], self._geoms[i]
+            rec, cw, _ = solver.forward(save='checkpoint', keep_segments=self.keep_segments)
+            res = rec._sdata.dev() - obs[i]._sdata.dev()
+            fval += 0.5 * (res.double() ** 2).sum()
+            r = Receiver(name='res', grid=self.model.grid, time_range=g_i.time_axis, coordinates=g_i.rec_positions)
+            r._sdata.adopt_dev(res)
+            solver.gradient(rec=r, u=cw, grad=self.grad)
+            del cw
+        self.buf[-1:] = fval.float()
+        dist.all_reduce_sum(self.buf)
+        if not host:
+            return self.buf[-1], self.grad
+        if self._host is None:
+            self._host = torch.empty(self.buf.shape, dtype=torch.float32).pin_memory()
+        self._host.copy_(self.buf)
+        h = self._host.numpy()
+        grid = self.model.grid
+        g = h[:-1].reshape(grid.slice_shape)[tuple(slice(0, n) for n in grid.shape)]
+        return float(h[-1]), g
