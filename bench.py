@@ -431,6 +431,8 @@ def layered3d(args, world, rank, local, lib, headline):
         sv = fwi.StreamingSurvey(geom)
         obs = sv.forward(vp=vp_true)                         # untimed set-up: observed data, device resident
         host_obs = {i: np.array(r.data) for i, r in obs.items()} if with_e2e else None
+        if with_e2e:
+            sv.host_buffer()                                 # pinned (f, g) mirror: allocated outside the timed region
         for r in obs.values():
             r._sdata.dev()
         if warm:

@@ -246,6 +246,8 @@ __global__ void __launch_bounds__(TMAX, 1) res2d_lat_kernel(const __grid_constan
     const int nsvc = max(ncell, itp_cnt);
     const int svc0 = (max((int)blockDim.x - ((nsvc + 31) & ~31), 0) / 2) & ~31;        // service roles centred in the CTA
     const int stid = (tid >= svc0) ? tid - svc0 : tid + (int)blockDim.x - svc0;
+    const bool needs_halo = (tactive && ((lr0 < R && crank > 0) || (lr0 + P - 1 + R >= rows_valid && crank < a.C - 1))) ||
+                            (stid < itp_cnt);
     int gj0 = 0, gj1 = 0;
     if (stid < ncell) { gj0 = a.inj_cptr[cell_base + stid] - con0; gj1 = a.inj_cptr[cell_base + stid + 1] - con0; }
     // receiver tables (forward)
@@ -372,6 +374,10 @@ __global__ void __launch_bounds__(TMAX, 1) res2d_lat_kernel(const __grid_constan
                 injn[s] = v;
             }
 
+        // the neighbours' boundary rows of the previous step: only the threads that read halo rows wait for them (the
+        // strips next to the CTA's edges and the receiver-recording threads); every other warp starts its rows right
+        // away, so the flight time of the pushes and the skew between neighbouring CTAs hide behind interior work
+        if (needs_halo && step > 0) mbar_wait(hbar + 8u * ((step - 1) & 1), (uint32_t)((step - 1) >> 1) & 1u);
         if (MODE == 0 && a.rec) {
             // rec[t][p] = sum_c w_c u[t][c]   (operators.py:137)
             for (int i = stid; i < itp_cnt; i += blockDim.x) {
@@ -518,13 +524,13 @@ __global__ void __launch_bounds__(TMAX, 1) res2d_lat_kernel(const __grid_constan
         }
         cp_async_wait_all();                                          // this thread's part of the staged value row
         __syncthreads();                                              // u[t+1] rows, staging buffers written
-        mbar_wait(hbar + 8u * (step & 1), (uint32_t)(step >> 1) & 1u);       // neighbours' boundary rows have landed
         { uint32_t x = cur_s; cur_s = nxt_s; nxt_s = x; }
         { uint32_t x = prv_c; prv_c = prv_n; prv_n = x; }
         { uint32_t x = nex_c; nex_c = nex_n; nex_n = x; }
         hidx0 += hstep4;
     }
 
+    if (nsteps > 0) mbar_wait(hbar + 8u * ((nsteps - 1) & 1), (uint32_t)((nsteps - 1) >> 1) & 1u);   // last pushes have landed
     cluster.sync();       // no CTA leaves while a neighbour could still address its shared memory
     if (a.out) {
         float *out = a.out + (int64_t)shot * (int64_t)(a.wx1 - a.wx0) * hq;

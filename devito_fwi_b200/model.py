@@ -15,8 +15,7 @@ import numpy as np
 
 from .grid import Grid, Function, Constant, mmax, mmin
 
-__all__ = ['SeismicModel', 'Model', 'ModelElastic', 'ModelViscoelastic', 'ModelViscoacoustic',
-           'initialize_damp', 'initialize_function']
+__all__ = ['SeismicModel', 'Model', 'initialize_damp', 'initialize_function']
 
 _UNSUPPORTED = ('vs', 'epsilon', 'delta', 'theta', 'phi', 'qp', 'qs', 'lam', 'mu')
 
@@ -259,6 +258,3 @@ class SeismicModel(GenericModel):
 
 
 Model = SeismicModel
-ModelElastic = SeismicModel
-ModelViscoelastic = SeismicModel
-ModelViscoacoustic = SeismicModel

@@ -292,6 +292,8 @@ class ResidentSurvey(object):
         nzq4 = 4 * ((self.grid.shape[1] + 3) // 4)
         sz = np.zeros(nzq4, dtype=np.float32)
         sz[:pz.size] = pz / self.dt
+        self._damp_ref = np.array(model.damp._buf.host_ro())
+        model.damp._buf.dev()
         self.sx = torch.from_numpy((px / self.dt).astype(np.float32)).cuda()
         self.sz = torch.from_numpy(sz).cuda()
         # source wavelets [nshots][nt][1] and maps
@@ -328,8 +330,32 @@ class ResidentSurvey(object):
         return plan_model(model.grid, so, model.nbl) is not None
 
     # ------------------------------------------------------------------
+    @property
+    def nbytes(self):
+        """Device bytes held by this survey (history, records, accumulators)."""
+        return sum(t.numel() * t.element_size() for t in (self.hist, self.illum, self.grad, self.rec, self.B)
+                   if t is not None)
+
+    def _check_model(self):
+        """The survey froze dt, the damping profiles and the wavelet at construction (they are geometry-only in the
+        reference's drivers): refuse to run on a model that has moved away from them."""
+        model = self.model
+        dt_now = float(model.critical_dt)         # raises ValueError when a user dt exceeds the CFL limit (model.py:366-369)
+        if abs(dt_now - self.dt) > 1e-6 * abs(self.dt):
+            raise ValueError("model.critical_dt changed from %g to %g since this survey was built" % (self.dt, dt_now))
+        buf = model.damp._buf
+        if buf._newer == 'host':                  # the host view of damp was handed out since the last check
+            if not np.array_equal(buf._host, self._damp_ref):
+                import warnings
+                warnings.warn("model.damp.data was edited after the resident survey was built: the SM-resident engine "
+                              "keeps using the separable profile of model.py:31-49; set fwi.ENGINE = 'stream' for a "
+                              "custom damping field")
+                self._damp_ref = np.array(buf._host)       # warn once per edit
+            buf.dev()                             # device copy current again: the flag is cleared
+
     def set_model(self, vp_dev=None):
         """(Re)compute B = dt^2 vp^2 from the model's current velocity."""
+        self._check_model()
         vp_dev = self.model.vp._buf.dev() if vp_dev is None else vp_dev
         _lib.check(_lib.lib().b2fwi_res2d_prepare(ctypes.byref(self.gs), _ptr(vp_dev), ctypes.c_float(self.dt),
                                                   _ptr(self.B), _stream()))

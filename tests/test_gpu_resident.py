@@ -298,3 +298,24 @@ def test_objective_with_observed_data_on_another_time_axis():
     assert len(res2) == 2 and np.asarray(res2[0]).shape == (g_init.nt, 300)
     print("resampled observed data: f %.3e g %.3e" % (abs(f2 - f1) / f1, rel_l2(g2, g1)))
     assert abs(f2 - f1) <= 1e-4 * f1 and rel_l2(g2, g1) <= 2 * TOL_GRAD
+
+
+def test_residuals_are_snapshots_and_line_search_evaluations_return_fval_only():
+    """The residuals of one evaluation must survive later evaluations on the same cached survey (the reference returns
+    independent arrays; a line search evaluates the objective again before anyone looks at them), and a
+    calc_grad=False evaluation returns the objective with a zero gradient (minimize.py:59-86)."""
+    from devito_fwi_b200 import configs, fwi
+    g_true, g_init = configs.circle(space_order=4, nsrc=2)
+    obs = fwi.fm_multi(g_true)
+    nbl = g_init.model.nbl
+    x0 = (1. / (g_init.model.vp.data[nbl:-nbl, nbl:-nbl].astype(np.float64) ** 2)).ravel()
+    f1, g1, r1 = fwi.fwi_loss(x0, g_init, obs, fwi.least_square)
+    f2, g2, r2 = fwi.fwi_loss(x0 * 1.03, g_init, obs, fwi.least_square, calc_grad=False)
+    assert f2 != f1 and not g2.any() and g1.any()
+    first = [np.asarray(r).copy() for r in r1]          # read only now, after the second evaluation
+    f3, g3, r3 = fwi.fwi_loss(x0, g_init, obs, fwi.least_square)
+    assert f3 == f1 and np.array_equal(g3, g1)
+    for a, b in zip(first, r3):
+        assert np.array_equal(a, np.asarray(b))
+    assert not np.array_equal(first[0], np.asarray(r2[0]))
+    assert float(0.5 * sum(np.sum(np.float64(a) ** 2) for a in first)) == pytest.approx(f1, rel=1e-6)
