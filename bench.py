@@ -734,18 +734,21 @@ def extra_2d():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    def objective(name, g_true, g_init, dw_geom, mask):
+    def objective(name, g_true, g_init, dw_geom, mask, misfit=None):
+        misfit = misfit or fwi.least_square
         model = g_init.model
         obs = fwi.fm_multi(g_true)
         dw = fwi.fm_multi(dw_geom) if dw_geom is not None else None
         nbl = model.nbl
         x0 = (1. / (model.vp.data[nbl:-nbl, nbl:-nbl].astype(np.float64) ** 2)).ravel()
-        ms = ev_time(lambda: fwi.fwi_loss(x0, g_init, obs, fwi.least_square, dw, mask, True, True))
+        ms = ev_time(lambda: fwi.fwi_loss(x0, g_init, obs, misfit, dw, mask, True, True))
         work = 2.0 * np.prod(model.grid.shape) * (g_init.nt - 2) * g_init.nsrc
         svs = fwi._resident_surveys(g_init, list(range(g_init.nsrc)))
         out[name] = {"grid": list(model.grid.shape), "so": model.space_order, "nt": g_init.nt, "shots": g_init.nsrc,
                      "ms_per_objective_gradient": round(ms, 3), "gpts_per_s": round(work / ms / 1e6, 1),
                      "shots_per_s": round(g_init.nsrc / ms * 1e3, 1),
+                     "misfit": getattr(misfit, '__name__', type(misfit).__name__) + (
+                         "(method=%s)" % misfit.method if hasattr(misfit, 'method') else ""),
                      "launch_groups_shots_x_cluster": [[sv.nshots, int(sv.plan.cluster)] for sv in svs] if svs else None}
         fwi._SURVEYS.clear()
 
@@ -755,6 +758,10 @@ def extra_2d():
     objective("circle_fwi_so4", g_true, g_init, None, None)
     g_true, g_init, g_const, mask = configs.marmousi2()
     objective("marmousi2_fwi_L2", g_true, g_init, g_const, mask)
+    # BASELINE.json configs[3] as the reference runs it (marmousi2_fwi.py:131-132): back-and-forth W2 of whole records
+    from devito_fwi_b200.misfit import qWasserstein
+    objective("marmousi2_fwi_QW2D", g_true, g_init, g_const, mask,
+              qWasserstein(method='2d', gamma=1.01, num_steps=15, step_scale=4.))
     g_true, g_init, g_const, _ = configs.marmousi(nsrc=21, tn=4500.)
     ms = ev_time(lambda: [fwi.fm_multi(g) for g in (g_true, g_init, g_const)])
     model = g_true.model

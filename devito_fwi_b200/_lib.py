@@ -12,7 +12,10 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libb2fwi.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "stream_kernels.cu", "stream_tma.cu", "resident2d.cu", "resident2d_lat.cu", "resident2d_lat_r2.cu",
-           "resident2d_lat_r3.cu", "resident2d_lat_r4.cu", "res2d_api.cu"]
+           "resident2d_lat_r3.cu", "resident2d_lat_r4.cu", "res2d_api.cu", "qw2d.cu"]
+# per-source extra flags: the QW2D solver follows the reference's C arithmetic, which is built without FMA contraction
+EXTRA_FLAGS = {"qw2d.cu": ["-fmad=false"]}
+LINK_FLAGS = ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(_ROOT, "include")]
@@ -64,7 +67,7 @@ def build(verbose=False, force=False):
         procs = []
         for src in sources():
             obj = os.path.join(tmp, os.path.basename(src)[:-3] + ".o")
-            cmd = ["nvcc"] + flags + ["-c", "-o", obj, src]
+            cmd = ["nvcc"] + flags + EXTRA_FLAGS.get(os.path.basename(src), []) + ["-c", "-o", obj, src]
             procs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs, log = [], ""
         for obj, pr in procs:
@@ -73,7 +76,7 @@ def build(verbose=False, force=False):
             if pr.returncode != 0:
                 raise B2fwiError("nvcc failed:\n" + log)
             objs.append(obj)
-        res = subprocess.run(["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + objs, stdout=subprocess.PIPE,
+        res = subprocess.run(["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + objs + LINK_FLAGS, stdout=subprocess.PIPE,
                              stderr=subprocess.STDOUT, text=True)
         if res.returncode != 0:
             raise B2fwiError("nvcc link failed:\n" + res.stdout)
@@ -116,6 +119,9 @@ PROTOTYPES = {
     "b2fwi_w1d_misfit": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, ctypes.c_double, _P, _P, _P, _P]),
     "b2fwi_w1d_scratch_bytes": (ctypes.c_int64, [_I, _I, _I]),
     "b2fwi_l2_misfit": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, _P, _P, _P, _P]),
+    "b2fwi_qw2d_misfit": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, ctypes.c_double, _I, _F, _P, _P, _P, _P, _P]),
+    "b2fwi_qw2d_scratch_bytes": (ctypes.c_int64, [_I, _I, _I]),
+    "b2fwi_qw2d_debug_step": (ctypes.c_int, [_I, _I, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P]),
 }
 
 

@@ -388,6 +388,18 @@ def _is_w1d(misfit_func):
     return _is_qw(misfit_func, '1d')
 
 
+def _is_w2d(misfit_func):
+    """qWasserstein(trans_type='linear', method='2d'): the back-and-forth solver misfit/QW2D (bfm.py:145-193)."""
+    return _is_qw(misfit_func, '2d')
+
+
+def _bfm_params(misfit_func):
+    """(num_steps, step_scale) of a qWasserstein object: the reference keeps them on its `bfm` solver
+    (misfit/misfit.py:17, bfm.py:149-154), devito_fwi_b200.misfit.qWasserstein on itself."""
+    holder = getattr(misfit_func, 'bfm', None) or misfit_func
+    return int(getattr(holder, 'num_steps')), float(getattr(holder, 'step_scale'))
+
+
 def _stack_dev(receivers, shots, cache_owner, tag, stream=None, after=None):
     """[nshots, nt, nrec] device tensor of a list of Receivers; re-used while the SAME list object is
     passed again and no record's host view has been handed out since (``.data`` access = possibly new
@@ -429,8 +441,8 @@ def _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_gr
     import torch
     lib = _lib.lib()
     shots = survey.shots
-    w1d = _is_w1d(misfit_func)
-    l2 = _is_l2(misfit_func) or w1d          # misfits evaluated on the device
+    w1d, w2d = _is_w1d(misfit_func), _is_w2d(misfit_func)
+    l2 = _is_l2(misfit_func) or w1d or w2d   # misfits evaluated on the device
     if l2 and getattr(survey, '_copy_stream', None) is None:
         survey._copy_stream = torch.cuda.Stream()
         survey._misfit_done = None
@@ -460,6 +472,16 @@ def _objective_resident(survey, geometry, obs, misfit_func, direct_wave, calc_gr
             _lib.check(lib.b2fwi_w1d_misfit(_ptr(syn), _ptr(obs_d), _ptr(dw_d), nt, nrec, ns,
                                             ctypes.c_double(float(misfit_func.gamma)), _ptr(survey._res),
                                             _ptr(survey._fval), _ptr(survey._w1d_scratch), _stream()))
+        elif w2d:
+            ns, nt, nrec = syn.shape
+            if getattr(survey, '_w2d_scratch', None) is None:
+                nbytes = int(lib.b2fwi_qw2d_scratch_bytes(nt, nrec, ns))
+                survey._w2d_scratch = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+            num_steps, step_scale = _bfm_params(misfit_func)
+            _lib.check(lib.b2fwi_qw2d_misfit(_ptr(syn), _ptr(obs_d), _ptr(dw_d), nt, nrec, ns,
+                                             ctypes.c_double(float(misfit_func.gamma)), num_steps,
+                                             ctypes.c_float(step_scale), _ptr(survey._res), _ptr(survey._fval), None,
+                                             _ptr(survey._w2d_scratch), _stream()))
         else:
             _lib.check(lib.b2fwi_l2_misfit(_ptr(syn), _ptr(obs_d), _ptr(dw_d), syn.numel(), _ptr(survey._res),
                                            _ptr(survey._fval), _ptr(survey._scratch), _stream()))

@@ -279,6 +279,29 @@ int b2fwi_w1d_misfit(const float *syn, const float *obs, const float *dw, int32_
                      double gamma, float *adjsrc_out, double *fval_out, void *scratch, void *stream);
 int64_t b2fwi_w1d_scratch_bytes(int32_t nt, int32_t nrec, int32_t nshots);
 
+/*
+ * On-device 2-D quadratic-Wasserstein misfit of whole shot records: qWasserstein(trans_type='linear', method='2d')
+ * of misfit/misfit.py:11-104, i.e. the back-and-forth optimal-transport solver misfit/QW2D/src/fot2d.c
+ * (compute_l2_fot2d :514-606, fotGradient2d :608-656) that the reference runs per shot as a subprocess over files
+ * (misfit/bfm.py:145-193), with the direct-wave subtraction of fwi.py:146-150 (dw nullable).
+ * syn, obs, dw, adjsrc_out: [nshots][nt][nrec] fp32 (the solver's n1 = nrec, n2 = nt). Per record: positivity shift
+ * c = gamma*max(0, -min), densities normalised to unit mean, `num_steps` back-and-forth iterations with initial step
+ * step_scale / max density (marmousi2_fwi.py:131-132: gamma=1.01, num_steps=15, step_scale=4);
+ * adjsrc_out = (dual - <mu, dual>) / mean(f) / mass;  fval_out[0] += sum over records of the W2 value;
+ * loss_out (nullable): [nshots] per-record values. scratch: b2fwi_qw2d_scratch_bytes() bytes. Uses cuFFT (DCTs of
+ * the Poisson solves); its plans are cached inside the library per record shape.
+ */
+int b2fwi_qw2d_misfit(const float *syn, const float *obs, const float *dw, int32_t nt, int32_t nrec, int32_t nshots,
+                      double gamma, int32_t num_steps, float step_scale, float *adjsrc_out, double *fval_out,
+                      float *loss_out, void *scratch, void *stream);
+int64_t b2fwi_qw2d_scratch_bytes(int32_t nt, int32_t nrec, int32_t nshots);
+/* One step of the solver on caller-provided single-record fields [nt][nrec] (diagnostics and the stage-by-stage
+ * parity tests): op 0 out = c-transform(a) (fot2d.c:157-183); op 1 a += sigma * Poisson(b - c), scal[0] = H^-1
+ * residual (fot2d.c:479-503); op 2 out = push-forward of density b by grad a (fot2d.c:290-478); op 3 scal[0] = W2
+ * value of (phi a, dual b, mu c, nu d) (fot2d.c:519-531). scratch: b2fwi_qw2d_scratch_bytes(nt, nrec, 1). */
+int b2fwi_qw2d_debug_step(int32_t op, int32_t nt, int32_t nrec, float *a, float *b, float *c, float *d, float sigma,
+                          float *out, float *scal, void *scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
