@@ -3,15 +3,23 @@ fit in HBM (3-D models).  Replaces pyrevolve / examples.checkpointing of the ref
 (seismic/acoustic/wavesolver.py:188-201) with a two-level scheme that lives entirely in HBM:
 
   pass 1  forward sweep on a 3-slot ring; before each segment of S steps the two live slices are
-          copied to a checkpoint (device-to-device);
-  pass 2  segments in reverse order: restore the checkpoint, recompute the segment while the
-          forward kernel also stores u.dt2 per step into an S-slice buffer, then run the
-          adjoint + imaging sweep over the segment reading one history value per point.
+          copied to a checkpoint (device-to-device). The LAST K steps run in history mode instead: the
+          sweep writes u[t+1] into a K+2-slice buffer rather than the ring, which costs no extra traffic,
+          so K is simply as large as the spare HBM allows (``keep='auto'``);
+  pass 2  the kept steps first, then the segments in reverse order: restore the checkpoint into the first
+          two slices of an S+2-slice buffer, recompute the segment in history mode (a PLAIN forward sweep:
+          20 B per point, nothing but the wavefield is written), then run the adjoint + imaging sweep over
+          the segment reading ONE history value per point.
 
-The forward kernels are deterministic, so the recomputed wavefield - and therefore the gradient -
-is bitwise identical to the one obtained from a full saved history (tests/test_gpu_parity.py).
-S ~ sqrt(2 * steps) minimises (2 * n_segments + S) slices of HBM. Spare HBM can be spent on keeping u.dt2 of
-further trailing segments from pass 1 (``keep_segments=n`` or ``'auto'``), which are then not recomputed.
+The imaging sum is taken by parts (B2FWI_HIST_UVDT2, include/b2fwi.h):
+    sum_t u.dt2[t] v[t]  =  sum_t u[t] v.dt2[t]  +  (u[M+1] v[M] - u[M] v[M+1] - u[m] v[m-1] + u[m-1] v[m]) / dt^2
+with v.dt2 formed inside the adjoint sweep from the three adjoint levels it holds anyway. Storing u.dt2 instead
+(round 1) made the recompute sweep write a second array: 76 B per point-step for the whole shot gradient against
+~66 now. The boundary term vanishes for the FWI gradient (u[m-1] = u[m] = 0 and v starts from rest); for a
+caller-supplied adjoint state ``v`` the M-part is added explicitly below.
+
+The forward kernels are deterministic, so every segmentation gives the bitwise same gradient; against the
+full-history imaging (u.dt2 from three saved slices) it differs by fp32 rounding only (tests/test_gpu_parity.py).
 
 ``forward(save='checkpoint')`` runs pass 1 while it records the receivers, and ``gradient(rec, u=<its result>)``
 then only needs pass 2: forward + recompute + adjoint = 3 sweeps per shot gradient instead of the 4 of the
@@ -23,7 +31,9 @@ import math
 from . import _lib
 from .sparse import sparse_map
 
-__all__ = ['checkpointed_gradient', 'checkpointed_forward', 'CheckpointedWavefield', 'plan_segments']
+__all__ = ['checkpointed_gradient', 'checkpointed_forward', 'CheckpointedWavefield', 'plan_segments', 'plan_keep']
+
+HIST_UVDT2 = 3          # include/b2fwi.h
 
 
 def plan_segments(time_m, time_M, segment=None):
@@ -34,48 +44,82 @@ def plan_segments(time_m, time_M, segment=None):
     return [(ta, min(ta + S - 1, time_M)) for ta in range(time_m, time_M + 1, S)]
 
 
+def plan_keep(steps, free_slices, segment=None, reserve_slices=8):
+    """(K, S): how many trailing steps keep their wavefield from pass 1 and the segment length of the rest, for
+    ``free_slices`` slices of spare HBM. Footprint: K + 2 (kept) + S + 2 (one recomputed segment) +
+    2 * ceil((steps - K) / S) (checkpoints) + reserve (adjoint ring, gradient, records). Pure function (CPU tests)."""
+    best = (0, int(segment) if segment else max(1, int(math.ceil(math.sqrt(2.0 * max(steps, 1))))))
+    if steps <= 0:
+        return best
+    cands = [int(segment)] if segment else sorted(set(
+        max(1, int(round(f * math.sqrt(2.0 * steps)))) for f in (0.5, 0.7, 0.85, 1.0, 1.2, 1.5, 2.0)))
+    best_k = -1
+    for S in cands:
+        # largest K with K + 2 + S + 2 + 2*ceil((steps-K)/S) + reserve <= free_slices
+        lo, hi = 0, steps
+        while lo < hi:
+            K = (lo + hi + 1) // 2
+            rest = steps - K
+            need = K + 2 + (S + 2 if rest > 0 else 0) + 2 * int(math.ceil(rest / float(S))) + reserve_slices
+            if need <= free_slices:
+                lo = K
+            else:
+                hi = K - 1
+        if lo > best_k:
+            best_k, best = lo, (lo, S)
+    return best
+
+
 class CheckpointedWavefield(object):
     """What ``AcousticWaveSolver.forward(save='checkpoint')`` returns in place of a saved TimeFunction:
-    the checkpoints of pass 1 (two slices per segment) and u.dt2 of the last segment, so that
+    the checkpoints of pass 1 (two slices per segment) and the wavefield of the last K steps, so that
     ``gradient(rec, u=<this>)`` goes straight to pass 2 - the forward sweep that produced the synthetic
     data is not repeated (the reference's pyrevolve branch runs it a second time, wavesolver.py:188-201)."""
     save = None
 
-    def __init__(self, solver, src, vp_dev, coef, dt, nt, time_m, time_M, segs, ring, ckpt, segbuf, nkeep, S):
+    def __init__(self, solver, src, vp_dev, coef, dt, nt, time_m, time_M, segs, ring, ckpt, segbuf, keepbuf, tk, S):
         self.solver, self.src, self.vp_dev, self.coef, self.dt = solver, src, vp_dev, coef, dt
         self.nt, self.time_m, self.time_M, self.segs = nt, time_m, time_M, segs
-        self.ring, self.ckpt, self.segbuf = ring, ckpt, segbuf
-        self.nkeep, self.S = nkeep, S      # u.dt2 of the last nkeep segments is already in segbuf (S slices each)
+        self.ring, self.ckpt, self.segbuf, self.keepbuf = ring, ckpt, segbuf, keepbuf
+        self.tk, self.S = tk, S            # steps tk .. time_M live in keepbuf: slice i holds u[tk - 1 + i]
+
+    @property
+    def nkeep_steps(self):
+        return max(self.time_M - self.tk + 1, 0)
 
     @property
     def nbytes(self):
-        return sum(t.numel() * 4 for t in (self.ring, self.ckpt, self.segbuf))
+        return sum(t.numel() * 4 for t in (self.ring, self.ckpt, self.segbuf, self.keepbuf) if t is not None)
 
 
-HBM_FRACTION = 0.75     # share of the free HBM that stored u.dt2 segments may take (the rest: v, grad, records)
+HBM_FRACTION = 0.85     # share of the free HBM the pass-1 history may take under keep='auto'
 
 
-def _keep_segments(nseg, S, slice_bytes, reserve_slices=10):
-    """How many trailing segments can keep their u.dt2 from pass 1 (each one saves a recompute sweep of S steps
-    at the price of 4 B/pt more traffic in pass 1): as many as fit in HBM_FRACTION of what is free."""
+def _free_slices(slice_bytes):
     import torch
     free = torch.cuda.mem_get_info()[0] + torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
-    budget = HBM_FRACTION * free - reserve_slices * slice_bytes
-    return int(max(1, min(nseg, budget // (S * slice_bytes))))
+    return int(HBM_FRACTION * free // slice_bytes)
+
+
+def _hist_ptr(buf, t0, slice_elems):
+    """Pointer such that (ptr + t * slice) is the slice of time level t when buf[0] holds level t0
+    (b2fwi_forward save=1 addresses u + t * elems; only levels >= t0 are touched)."""
+    return ctypes.c_void_p(buf.data_ptr() - int(t0) * int(slice_elems) * 4)
 
 
 def checkpointed_forward(solver, src, rec, vp, dt, illum=None, **kwargs):
-    """Pass 1: forward sweep on a 3-slot ring with receiver recording (and the source illumination),
-    checkpointing the two live slices before every segment; the last ``keep_segments`` segments (default 1;
-    ``'auto'``: as many as fit in HBM_FRACTION of the free HBM) store u.dt2 right away and are not recomputed by
-    pass 2. Returns a CheckpointedWavefield."""
+    """Pass 1: forward sweep with receiver recording (and the source illumination), checkpointing the two live
+    slices before every segment; the last K steps write the wavefield into the history buffer of pass 2.
+    ``keep_segments``: None / 'auto' = K as large as HBM_FRACTION of the free HBM allows, an int n = the last n
+    segments, 0 = minimal footprint (the last segment only). Returns a CheckpointedWavefield."""
     import torch
     from .wavesolver import _ptr, _stream
     lib = _lib.lib()
     nt = min(rec.nt, src.nt) if rec is not None else src.nt
     time_m, time_M = solver._time_bounds(kwargs, nt)
-    segs = plan_segments(time_m, time_M, kwargs.pop('segment', None))
+    segment = kwargs.pop('segment', None)
     keep = kwargs.pop('keep_segments', None)
+    steps = max(time_M - time_m + 1, 0)
     grid = solver.model.grid
     g = solver._gs()
     vp_dev = solver._vp_dev(vp)
@@ -86,39 +130,53 @@ def checkpointed_forward(solver, src, rec, vp, dt, illum=None, **kwargs):
     rec_dev = rec._sdata.dev(write=True) if rec is not None else None
     illum_dev = illum._buf.dev(write=True) if illum is not None else None
     slice_shape = grid.slice_shape
+    elems = grid.slice_elems
     ring = torch.zeros((3,) + slice_shape, dtype=torch.float32, device='cuda')
-    nseg = len(segs)
-    S = max((tb - ta + 1) for ta, tb in segs) if segs else 1
-    ckpt = torch.empty((max(nseg, 1), 2) + slice_shape, dtype=torch.float32, device='cuda')
-    if keep is None:
-        nkeep = 1                          # minimal footprint: only the last segment's u.dt2 comes from pass 1
-    elif keep == 'auto':
-        nkeep = _keep_segments(nseg, S, grid.slice_elems * 4)
+    if keep is None or keep == 'auto':
+        K, S = plan_keep(steps, _free_slices(elems * 4), segment)
     else:
-        nkeep = max(1, min(int(keep), max(nseg, 1)))
-    try:
-        segbuf = torch.empty((nkeep * S,) + slice_shape, dtype=torch.float32, device='cuda')
-    except torch.cuda.OutOfMemoryError:
-        nkeep = 1
-        segbuf = torch.empty((S,) + slice_shape, dtype=torch.float32, device='cuda')
-    k0 = nseg - nkeep                      # first segment whose u.dt2 is kept
+        S = int(segment) if segment else max(1, int(math.ceil(math.sqrt(2.0 * max(steps, 1)))))
+        K = min(steps, max(1, int(keep)) * S)
+    K = max(K, min(S, steps))                       # at least the last segment comes from pass 1
+    while True:
+        tk = time_M - K + 1                          # first kept step
+        segs = plan_segments(time_m, tk - 1, S)
+        try:
+            ckpt = torch.empty((len(segs), 2) + slice_shape, dtype=torch.float32, device='cuda') if segs else None
+            segbuf = torch.empty((S + 2,) + slice_shape, dtype=torch.float32, device='cuda') if segs else None
+            keepbuf = torch.empty((K + 2,) + slice_shape, dtype=torch.float32, device='cuda') if K > 0 else None
+            break
+        except torch.cuda.OutOfMemoryError:
+            ckpt = segbuf = keepbuf = None
+            torch.cuda.empty_cache()
+            if K <= min(S, steps):
+                raise
+            K = max(min(S, steps), K // 2)
     cdt = ctypes.c_float(dt)
-    for k, (ta, tb) in enumerate(segs):
-        if k < k0:                          # kept segments are never restored: no checkpoint needed
-            ckpt[k, 0].copy_(ring[(ta - 1) % 3])
-            ckpt[k, 1].copy_(ring[ta % 3])
+
+    def sweep(ta, tb, u_ptr, save, ill):
         _lib.check(lib.b2fwi_forward(
             ctypes.byref(g), _ptr(vp_dev), _ptr(coef), cdt, nt, ta, tb,
             _ptr(src_dev), src_map.byref(), _ptr(rec_dev), rec_map.byref() if rec_map is not None else None,
-            _ptr(ring), 0, _ptr(illum_dev), _ptr(segbuf[(k - k0) * S:]) if k >= k0 else None, ta, _stream()))
+            u_ptr, save, ill, None, 0, _stream()))
+
+    for k, (ta, tb) in enumerate(segs):
+        ckpt[k, 0].copy_(ring[(ta - 1) % 3])
+        ckpt[k, 1].copy_(ring[ta % 3])
+        sweep(ta, tb, _ptr(ring), 0, _ptr(illum_dev))
+    if K > 0:
+        keepbuf[0].copy_(ring[(tk - 1) % 3])
+        keepbuf[1].copy_(ring[tk % 3])
+        sweep(tk, time_M, _hist_ptr(keepbuf, tk - 1, elems), 1, _ptr(illum_dev))
     return CheckpointedWavefield(solver, src, vp_dev, coef, dt, nt, time_m, time_M, segs, ring, ckpt, segbuf,
-                                 nkeep, S)
+                                 keepbuf, tk, S)
 
 
-def checkpointed_gradient(solver, rec, v, grad, vp, dt, checkpoints=None, **kwargs):
-    """Gradient with checkpointing; same results as ``jacobian_adjoint(rec, u_saved)``.
+def checkpointed_gradient(solver, rec, v, grad, vp, dt, checkpoints=None, v_from_rest=True, **kwargs):
+    """Gradient with checkpointing; same results as ``jacobian_adjoint(rec, u_saved)`` up to fp32 rounding.
     ``checkpoints``: the CheckpointedWavefield of an earlier ``forward(save='checkpoint')`` with the same
-    model; without it pass 1 is run here (the reference's behaviour)."""
+    model; without it pass 1 is run here (the reference's behaviour). ``v_from_rest=False``: the caller's ``v``
+    holds a non-zero adjoint state, whose boundary term of the summation by parts is added here."""
     from .wavesolver import _ptr, _stream, _Timer, BYTES_ADJ, BYTES_FWD
     lib = _lib.lib()
     timer = _Timer(solver._profile)
@@ -130,8 +188,9 @@ def checkpointed_gradient(solver, rec, v, grad, vp, dt, checkpoints=None, **kwar
         cw = checkpointed_forward(solver, src, None, vp, dt, time_m=tm, time_M=tM, segment=kwargs.pop('segment', None),
                                   keep_segments=kwargs.pop('keep_segments', None))
         cw.nt = nt_
-    nt, segs, ring, ckpt, segbuf = cw.nt, cw.segs, cw.ring, cw.ckpt, cw.segbuf
+    nt, segs, ckpt, segbuf, keepbuf = cw.nt, cw.segs, cw.ckpt, cw.segbuf, cw.keepbuf
     grid = solver.model.grid
+    elems = grid.slice_elems
     g = solver._gs()
     vp_dev, coef, src = cw.vp_dev, cw.coef, cw.src
     src_map = sparse_map(grid, src.coordinates.data)
@@ -140,23 +199,29 @@ def checkpointed_gradient(solver, rec, v, grad, vp, dt, checkpoints=None, **kwar
     rec_dev = rec._sdata.dev()
     v_dev = v._buf.dev(write=True)
     grad_dev = grad._buf.dev(write=True)
-    nseg = len(segs)
-    k0 = nseg - cw.nkeep
     cdt = ctypes.c_float(cw.dt)
-    for k in range(nseg - 1, -1, -1):
-        ta, tb = segs[k]
-        if k >= k0:                         # u.dt2 kept from pass 1
-            hist = segbuf[(k - k0) * cw.S:]
-        else:                               # restore the checkpoint and recompute the segment (kept ones are consumed)
-            hist = segbuf
-            ring[(ta - 1) % 3].copy_(ckpt[k, 0])
-            ring[ta % 3].copy_(ckpt[k, 1])
-            _lib.check(lib.b2fwi_forward(
-                ctypes.byref(g), _ptr(vp_dev), _ptr(coef), cdt, nt, ta, tb,
-                _ptr(src_dev), src_map.byref(), None, None, _ptr(ring), 0, None, _ptr(hist), ta, _stream()))
+
+    def adjoint(ta, tb, hist, t0):
         _lib.check(lib.b2fwi_gradient(
             ctypes.byref(g), _ptr(vp_dev), _ptr(coef), cdt, nt, ta, tb,
-            _ptr(rec_dev), rec_map.byref(), _ptr(hist), 2, ta, _ptr(v_dev), _ptr(grad_dev), _stream()))
+            _ptr(rec_dev), rec_map.byref(), _ptr(hist), HIST_UVDT2, t0, _ptr(v_dev), _ptr(grad_dev), _stream()))
+
+    if keepbuf is not None and cw.time_M >= cw.tk:
+        if not v_from_rest:
+            # grad += -(u[M+1] v[M] - u[M] v[M+1]) / dt^2 ; the m-part is zero: pass 1 starts from a zero ring
+            M = cw.time_M
+            inv_dt2 = 1.0 / (float(cw.dt) * float(cw.dt))
+            grad_dev.add_((keepbuf[-1] * v_dev[M % 3] - keepbuf[-2] * v_dev[(M + 1) % 3]) * (-inv_dt2))
+        adjoint(cw.tk, cw.time_M, keepbuf, cw.tk - 1)
+    for k in range(len(segs) - 1, -1, -1):
+        ta, tb = segs[k]
+        segbuf[0].copy_(ckpt[k, 0])
+        segbuf[1].copy_(ckpt[k, 1])
+        _lib.check(lib.b2fwi_forward(
+            ctypes.byref(g), _ptr(vp_dev), _ptr(coef), cdt, nt, ta, tb,
+            _ptr(src_dev), src_map.byref(), None, None, _hist_ptr(segbuf, ta - 1, elems), 1, None, None, 0,
+            _stream()))
+        adjoint(ta, tb, segbuf, ta - 1)
     steps = max(cw.time_M - cw.time_m + 1, 0)
     bpp = BYTES_ADJ + (1 if checkpoints is not None else 2) * BYTES_FWD
     summary = solver._summary('Gradient', timer.stop(), steps, bpp)

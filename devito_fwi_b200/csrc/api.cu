@@ -208,8 +208,9 @@ static int backward(const b2fwi_grid *g, const float *vp, const float *coef, flo
     int img = 0;
     if (grad) {
         B2_CHECK_ARG(hist != nullptr, "hist is NULL");
-        B2_CHECK_ARG(hist_kind == B2FWI_HIST_U || hist_kind == B2FWI_HIST_D2U, "bad hist_kind %d", hist_kind);
-        img = hist_kind;
+        B2_CHECK_ARG(hist_kind == B2FWI_HIST_U || hist_kind == B2FWI_HIST_D2U || hist_kind == B2FWI_HIST_UVDT2,
+                     "bad hist_kind %d", hist_kind);
+        img = (hist_kind == B2FWI_HIST_UVDT2) ? B2FWI_HIST_D2U : hist_kind;
     }
     cudaStream_t st = (cudaStream_t)stream;
     StepArgs a;
@@ -220,6 +221,7 @@ static int backward(const b2fwi_grid *g, const float *vp, const float *coef, flo
     a.inv_dt2 = 1.f / (dt * dt);
     a.chunk = pick_chunk(L);
     a.grad = grad;
+    a.hist_uv = (grad && hist_kind == B2FWI_HIST_UVDT2) ? 1 : 0;
     for (int time = time_M; time >= time_m; time--) {
         float *vn = v + (int64_t)((time - 1) % 3) * L.elems;
         const float *vc = v + (int64_t)(time % 3) * L.elems, *vq = v + (int64_t)((time + 1) % 3) * L.elems;
@@ -232,7 +234,8 @@ static int backward(const b2fwi_grid *g, const float *vp, const float *coef, flo
         }
         if ((rc = launch_step(L, a, img, st))) return rc;
         if (nrec > 0 &&
-            (rc = launch_inject(vn, vp, dt, rec + (int64_t)time * nrec, rec_map, nullptr, nullptr, nullptr, 0.f, st)))
+            (rc = launch_inject(vn, vp, dt, rec + (int64_t)time * nrec, rec_map, nullptr, nullptr, nullptr, a.inv_dt2, st,
+                                a.hist_uv ? grad : nullptr, a.hist_uv ? a.h1 : nullptr)))
             return rc;
         if (srca && nsrc > 0 && (rc = launch_interp(vc, srca + (int64_t)time * nsrc, src_map, st))) return rc;
     }

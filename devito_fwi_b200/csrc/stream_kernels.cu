@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
                     const float4 C = q[(j + QC) % NQ];
                     const float4 o = point_update<R, NDIM, SW>(a, q, j, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, zvalid);
                     F4W(a.out)[idx] = o;
-                    if (IMG != 0) F4W(a.grad)[idx] = img4(g4, IMG == 1 ? d2u4(h0, h1, h2, a.inv_dt2) : h1, C);
+                    if (IMG == 1) F4W(a.grad)[idx] = img4(g4, d2u4(h0, h1, h2, a.inv_dt2), C);
+                    if (IMG == 2) F4W(a.grad)[idx] = img4(g4, h1, a.hist_uv ? d2u4(prev, C, o, a.inv_dt2) : C);
                     if (a.illum) F4W(a.illum)[idx] = fma4(C, C, il);
                     if (a.d2u) {
                         float4 d = d2u4(prev, C, o, a.inv_dt2);
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256, 2) step3d_async_kernel(const __grid_const
             const float4 C = q[QC];
             const float4 o = point_update<R, 3, SW>(a, q, 0, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, zvalid);
             st4(a.out + own0 + pofs, o);
-            if (IMG == 2) st4(a.grad + own0 + pofs, img4(ax[768], ax[1024], C));
+            if (IMG == 2) st4(a.grad + own0 + pofs, img4(ax[768], ax[1024], a.hist_uv ? d2u4(prev, C, o, a.inv_dt2) : C));
             if (a.illum) st4(a.illum + own0 + pofs, fma4(C, C, il));
             if (a.d2u) {
                 float4 d = d2u4(prev, C, o, a.inv_dt2);
@@ -443,17 +444,20 @@ __global__ void inject_kernel(float *__restrict__ field, const float *__restrict
                               const int64_t *__restrict__ cell_off, const int32_t *__restrict__ cell_ptr,
                               const int32_t *__restrict__ contrib_pt, const float *__restrict__ contrib_w,
                               float *__restrict__ d2u, const float *__restrict__ cur,
-                              const float *__restrict__ prev, float inv_dt2)
+                              const float *__restrict__ prev, float inv_dt2,
+                              float *__restrict__ grad, const float *__restrict__ hist)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ncell) return;
     const int64_t off = cell_off[i];
     const float v = vp[off];
-    float f = field[off];
+    const float f0 = field[off];
+    float f = f0;
     for (int j = cell_ptr[i]; j < cell_ptr[i + 1]; j++)
         f += contrib_w[j] * vals[contrib_pt[j]] * dt * dt * v * v;
     field[off] = f;
     if (d2u) d2u[off] = d2u_of(prev[off], cur[off], f, inv_dt2);
+    if (grad) grad[off] = __fmaf_rn(-hist[off], __fmul_rn(__fsub_rn(f, f0), inv_dt2), grad[off]);
 }
 
 // out[p] = sum_c w_c * field[c]  (operators.py:137,176)
@@ -471,11 +475,13 @@ __global__ void interp_kernel(const float *__restrict__ field, float *__restrict
 }
 
 int launch_inject(float *field, const float *vp, float dt, const float *vals, const b2fwi_sparse *m,
-                  float *d2u, const float *cur, const float *prev, float inv_dt2, cudaStream_t st)
+                  float *d2u, const float *cur, const float *prev, float inv_dt2, cudaStream_t st,
+                  float *grad, const float *hist)
 {
     if (!m || m->ncell <= 0) return 0;
     inject_kernel<<<(m->ncell + 127) / 128, 128, 0, st>>>(field, vp, dt, vals, m->ncell, m->cell_off, m->cell_ptr,
-                                                        m->contrib_pt, m->contrib_w, d2u, cur, prev, inv_dt2);
+                                                        m->contrib_pt, m->contrib_w, d2u, cur, prev, inv_dt2,
+                                                        grad, hist);
     B2_CUDA(cudaGetLastError());
     count_launch();
     return 0;

@@ -15,6 +15,7 @@ struct StepArgs {
     // imaging condition (IMG != 0): grad += -u.dt2 * cur
     float *grad;
     const float *h0, *h1, *h2;  // IMG==1: u[t-1], u[t], u[t+1];  IMG==2: h1 = u.dt2[t]
+    int hist_uv;           // IMG==2 only: h1 = u[t] and the imaging factor is v.dt2[t] (B2FWI_HIST_UVDT2)
     float inv_dt2;
     // forward extras (nullable)
     float *illum;          // += cur^2
@@ -35,8 +36,11 @@ void tma_tile_shape(int R, int *tz, int *tr);
 bool tma_enabled(int img);
 void set_tma_mask(int mask);      // b2fwi_set_option("tma", mask): bit 0 forward, bit 1 adjoint + imaging
 int get_tma_mask();
+// d2u/cur/prev: patch u.dt2 at the injected cells (forward); grad/hist: imaging by parts (B2FWI_HIST_UVDT2) - the
+// sweep formed v.dt2 before the injection, the injected increment is added here: grad -= hist * dv / dt^2
 int launch_inject(float *field, const float *vp, float dt, const float *vals, const b2fwi_sparse *m,
-                  float *d2u, const float *cur, const float *prev, float inv_dt2, cudaStream_t st);
+                  float *d2u, const float *cur, const float *prev, float inv_dt2, cudaStream_t st,
+                  float *grad = nullptr, const float *hist = nullptr);
 int launch_interp(const float *field, float *out, const b2fwi_sparse *m, cudaStream_t st);
 int launch_coeffs(const Layout &L, const float *vp, const float *damp, float dt, float *coef, cudaStream_t st);
 int launch_accum_sq(const Layout &L, float *acc, const float *f, cudaStream_t st);

@@ -34,9 +34,10 @@ static __device__ __forceinline__ float4 ldt(SAddr s, int off)
 //   The pipeline is addressed circularly: plane offset i in -R..R lives in q[(j + R + i) % NQ] (j: rotation).
 //   W: anything carrying the Laplacian weights (StepArgs in constant memory, or StencilW pinned in registers).
 //   MASKZ = false: the caller guarantees c2 == 0 and u == 0 beyond nz (TMA zero fill), which makes the update 0 there.
-template <int R, int NDIM, int SW, bool MASKZ = true, class W = StepArgs, class TP = const float *>
-static __device__ __forceinline__ float4 point_update(const W &a, const float4 *q, int j, TP ctr,
-                                                     float4 prev, float4 c1, float4 c2, int zvalid)
+// (split in two so that a kernel short of registers can fetch prev / c1 / c2 AFTER the Laplacian: point_laplacian +
+// point_finish is point_update, operation for operation)
+template <int R, int NDIM, int SW, class W = StepArgs, class TP = const float *>
+static __device__ __forceinline__ float4 point_laplacian(const W &a, const float4 *q, int j, TP ctr)
 {
     constexpr int RZ4 = (R + 3) / 4, ZH = 4 * RZ4;
     constexpr int NQ = (NDIM == 3) ? 2 * R + 1 : 1;
@@ -86,7 +87,12 @@ static __device__ __forceinline__ float4 point_update(const W &a, const float4 *
     } else {
         l01 = make_float2(oa.y, ob.x); l23 = make_float2(ob.y, oc.x);
     }
-    const float4 lap = add4(add4(lp, lr), mk4(l01, l23));
+    return add4(add4(lp, lr), mk4(l01, l23));
+}
+
+template <bool MASKZ = true>
+static __device__ __forceinline__ float4 point_finish(float4 C, float4 lap, float4 prev, float4 c1, float4 c2, int zvalid)
+{
     // u+ = u + c1 (u - u-) + c2 L(u)
     const float4 t = fma4(c1, add4(C, make_float4(-prev.x, -prev.y, -prev.z, -prev.w)), C);
     float4 o = fma4(c2, lap, t);
@@ -96,6 +102,16 @@ static __device__ __forceinline__ float4 point_update(const W &a, const float4 *
         o.w = 0.f;
     }
     return o;
+}
+
+template <int R, int NDIM, int SW, bool MASKZ = true, class W = StepArgs, class TP = const float *>
+static __device__ __forceinline__ float4 point_update(const W &a, const float4 *q, int j, TP ctr,
+                                                     float4 prev, float4 c1, float4 c2, int zvalid)
+{
+    constexpr int NQ = (NDIM == 3) ? 2 * R + 1 : 1;
+    constexpr int QC = (NDIM == 3) ? R : 0;
+    const float4 lap = point_laplacian<R, NDIM, SW, W, TP>(a, q, j, ctr);
+    return point_finish<MASKZ>(q[(j + QC) % NQ], lap, prev, c1, c2, zvalid);
 }
 
 // Laplacian weights held in registers (filled by the kernel from a source ptxas cannot rematerialise)

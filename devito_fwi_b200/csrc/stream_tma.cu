@@ -80,7 +80,7 @@ struct TmaCfg {
     static constexpr int CUR_BYTES = SROWS * SW * 4;                       // one u[t] box
     static constexpr int CUR_STRIDE = (CUR_BYTES + 127) / 128 * 128;       // ring stage stride (TMA destinations: 128 B)
     static constexpr int PL_BYTES = TR * TZ * 4;                           // one pointwise-operand box
-    static constexpr int NARR = (IMG == 2) ? 4 : 3;                        // prev, c2, c1 [, u.dt2]
+    static constexpr int NARR = (IMG >= 2) ? 4 : 3;                        // prev, c2, c1 [, u.dt2]
     static constexpr int PCC_BYTES = NARR * PL_BYTES;
     // operand-ring stage of unroll slot j is the compile-time j % NPCC when the ring turns a whole, odd number of
     // times per group of NQ planes; otherwise stage and parity are carried in two registers
@@ -95,8 +95,11 @@ struct TmaCfg {
     static_assert(2 * NCUR + NPCC <= 64 && 2 + 3 * R <= 32, "barrier / weight slots");
 };
 
-// IMG: 0 forward sweep (EXTRAS: illumination / u.dt2 store), 2 adjoint sweep + imaging from stored u.dt2.
+// IMG: 0 forward sweep (EXTRAS: illumination / u.dt2 store), 2 adjoint sweep + imaging from stored u.dt2,
+// 3 adjoint sweep + imaging by parts from the stored wavefield itself (B2FWI_HIST_UVDT2: grad -= u[t] * v.dt2[t]).
 template <int R, int NPCC, int IMG, bool EXTRAS>
+// (544 threads = 17 warps are allocated as 20 - warps come in groups of four - so ptxas budgets 96 registers; a
+// direct __maxnreg__(120) compiles without the imaging variants' few spills but does not launch)
 __global__ void __launch_bounds__(TmaCfg<R, NPCC, IMG>::NTHREADS, 1)
 step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CUtensorMap m_cur,
                   const __grid_constant__ CUtensorMap m_prev, const __grid_constant__ CUtensorMap m_c1,
@@ -169,7 +172,7 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
                 tma_load_3d(dst, &m_prev, bar, ztile0, r0, p);
                 tma_load_3d(dst + C::PL_BYTES, &m_c2, bar, ztile0, r0, p);
                 if (!skip_c1) tma_load_3d(dst + 2 * C::PL_BYTES, &m_c1, bar, ztile0, r0, p);
-                if (IMG == 2) tma_load_3d(dst + 3 * C::PL_BYTES, &m_h1, bar, ztile0, r0, p);
+                if (IMG >= 2) tma_load_3d(dst + 3 * C::PL_BYTES, &m_h1, bar, ztile0, r0, p);
             };
             // fill both rings, in the order the planes are needed
             for (int k = 0; k < NCUR; k++) {
@@ -242,7 +245,7 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
                 float4 g4;
                 // imaging: grad goes through registers (the operand ring has no room for a fifth array); the load
                 // is issued before the barrier waits and consumed after the update
-                if (IMG == 2 && active) g4 = F4(a.grad)[idx];
+                if (IMG >= 2 && active) g4 = F4(a.grad)[idx];
                 // feed: plane i+R enters the register pipeline from its ring stage
                 const int sf = (j + R) % NQ;
                 if (!EDGE || i + R < ncur) {
@@ -262,20 +265,31 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
                     if (++ps == NPCC) { ps = 0; pp ^= 1u; }
                 }
                 const int p = p_begin + i;
-                const float4 prev = lds4(pc);
-                const float4 c2 = lds4(pc + C::PL_BYTES);
-                const float4 c1 = (p >= blo_p && p < bhi_p) ? one4 : lds4(pc + 2 * C::PL_BYTES);
-                float4 h1;
-                if (IMG == 2) h1 = lds4(pc + 3 * C::PL_BYTES);
-                // no z masking: beyond nz the TMA unit filled u[t], u[t-1] and c2 with zeros, so o == 0 there
-                const float4 o = point_update<R, 3, SW, false>(w, q, j, SAddr{ctr_s + (j % NCUR) * C::CUR_STRIDE},
-                                                               prev, c1, c2, 4);
+                float4 prev, c2, c1, h1, o;
+                if (IMG == 3) {
+                    // the by-parts imaging keeps u[t-1] alive to the end: fetch the pointwise operands after the
+                    // Laplacian instead of holding 16 registers across it (the variant is register-bound at 96)
+                    const float4 lap = point_laplacian<R, 3, SW>(w, q, j, SAddr{ctr_s + (j % NCUR) * C::CUR_STRIDE});
+                    prev = lds4(pc);
+                    c2 = lds4(pc + C::PL_BYTES);
+                    c1 = (p >= blo_p && p < bhi_p) ? one4 : lds4(pc + 2 * C::PL_BYTES);
+                    h1 = lds4(pc + 3 * C::PL_BYTES);
+                    o = point_finish<false>(q[(j + R) % NQ], lap, prev, c1, c2, 4);
+                } else {
+                    prev = lds4(pc);
+                    c2 = lds4(pc + C::PL_BYTES);
+                    c1 = (p >= blo_p && p < bhi_p) ? one4 : lds4(pc + 2 * C::PL_BYTES);
+                    if (IMG == 2) h1 = lds4(pc + 3 * C::PL_BYTES);
+                    // no z masking: beyond nz the TMA unit filled u[t], u[t-1] and c2 with zeros, so o == 0 there
+                    o = point_update<R, 3, SW, false>(w, q, j, SAddr{ctr_s + (j % NCUR) * C::CUR_STRIDE}, prev, c1, c2, 4);
+                }
                 // stage j (u[t] plane i) and the operand stage are free again
                 __syncwarp();
                 if (lane0) mbar_arrive(bar_em + 8 * (j % NCUR));
                 if (active) {
                     F4W(a.out)[idx] = o;
                     if (IMG == 2) F4W(a.grad)[idx] = img4(g4, h1, q[(j + R) % NQ]);
+                    if (IMG == 3) F4W(a.grad)[idx] = img4(g4, h1, d2u4(prev, q[(j + R) % NQ], o, a.inv_dt2));
                     if (EXTRAS) {
                         const float4 Cc = q[(j + R) % NQ];
                         if (a.illum) F4W(a.illum)[idx] = fma4(Cc, Cc, F4(a.illum)[idx]);
@@ -345,7 +359,7 @@ static int launch_tma(const StepArgs &a, cudaStream_t st)
     if ((rc = make_map(&m_prev, a.prev, a, C::TZ, C::TR))) return rc;
     if ((rc = make_map(&m_c1, a.c1, a, C::TZ, C::TR))) return rc;
     if ((rc = make_map(&m_c2, a.c2, a, C::TZ, C::TR))) return rc;
-    if ((rc = make_map(&m_h1, IMG == 2 ? a.h1 : a.c2, a, C::TZ, C::TR))) return rc;
+    if ((rc = make_map(&m_h1, IMG >= 2 ? a.h1 : a.c2, a, C::TZ, C::TR))) return rc;
     const int nchunks = (a.np + a.chunk - 1) / a.chunk;
     dim3 grid((a.nz + C::TZ - 1) / C::TZ, (a.nr + C::TR - 1) / C::TR, nchunks);
     kern<<<grid, C::NTHREADS, C::SMEM, st>>>(a, m_cur, m_prev, m_c1, m_c2, m_h1);
@@ -382,7 +396,7 @@ bool tma_enabled(int img) { return (g_tma & (img == 0 ? 1 : 2)) != 0 && encode_f
 template <int R, int NPCC>
 static int launch_tma_r(const StepArgs &a, int img, cudaStream_t st)
 {
-    if (img == 2) return launch_tma<R, NPCC, 2, false>(a, st);
+    if (img == 2) return a.hist_uv ? launch_tma<R, NPCC, 3, false>(a, st) : launch_tma<R, NPCC, 2, false>(a, st);
     return (a.illum || a.d2u) ? launch_tma<R, NPCC, 0, true>(a, st) : launch_tma<R, NPCC, 0, false>(a, st);
 }
 

@@ -241,14 +241,15 @@ class AcousticWaveSolver(object):
         lib = _lib.lib()
         dt = float(kwargs.pop('dt', self.dt))
         grad = grad or Function(name='grad', grid=self.model.grid)
+        v_from_rest = v is None            # a caller-supplied v is an initial adjoint state (ownership)
         v = v or TimeFunction(name='v', grid=self.model.grid,
                               time_order=2, space_order=self.space_order)
         vp = vp or self.model.vp
         from .checkpoint import checkpointed_gradient, CheckpointedWavefield
         if isinstance(u, CheckpointedWavefield):
-            return checkpointed_gradient(self, rec, v, grad, vp, dt, checkpoints=u, **kwargs)
+            return checkpointed_gradient(self, rec, v, grad, vp, dt, checkpoints=u, v_from_rest=v_from_rest, **kwargs)
         if checkpointing:
-            return checkpointed_gradient(self, rec, v, grad, vp, dt, **kwargs)
+            return checkpointed_gradient(self, rec, v, grad, vp, dt, v_from_rest=v_from_rest, **kwargs)
 
         if not u.save:
             raise ValueError("the gradient needs the saved forward wavefield: forward(save=True)")

@@ -72,6 +72,12 @@ typedef struct b2fwi_sparse {
 
 #define B2FWI_HIST_U 1    /* u_hist[nt][slice]: the saved wavefield itself (TimeFunction(save=nt)) */
 #define B2FWI_HIST_D2U 2  /* d2u[nt][slice]: slices of u.dt2 written by b2fwi_forward(d2u_out=...) */
+/* u_hist[nt][slice] again, but one history value per point and step: the imaging sum is taken by parts,
+ *   sum_t u.dt2[t] v[t] = sum_t u[t] v.dt2[t] + (u[M+1] v[M] - u[M] v[M+1] - u[m] v[m-1] + u[m-1] v[m]) / dt^2,
+ * and v.dt2[t] = (v[t+1] - 2 v[t] + v[t-1]) / dt^2 is formed from the three adjoint levels the sweep holds anyway.
+ * The caller owns the boundary term (zero when v starts from rest and u[m-1] = u[m] = 0: the FWI gradient).
+ * Checkpoint segments use it: the recompute sweep then writes nothing but the wavefield itself (checkpoint.py). */
+#define B2FWI_HIST_UVDT2 3
 
 int32_t b2fwi_version(void);
 const char *b2fwi_last_error(void);

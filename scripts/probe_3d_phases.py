@@ -41,4 +41,5 @@ phase("gradient_pass2", lambda: solver.gradient(rec=res, u=cw))
 phase("gradient_pass2_again", lambda: solver.gradient(rec=res, u=cw))
 stop = True
 out["steps"] = geom.nt - 2
+out["kept_steps"], out["segment"], out["segments"], out["cw_GB"] = cw.nkeep_steps, cw.S, len(cw.segs), round(cw.nbytes / 1e9, 1)
 print(json.dumps(out))

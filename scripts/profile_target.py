@@ -17,9 +17,9 @@ if what == "2d":
 else:
     geom = configs.layered3d(n=512, space_order=8, rec_decimate=8)
     solver = b.AcousticWaveSolver(geom.model, geom, space_order=8)
-    # 8 time steps in 2 checkpoint segments: forward (4 plain + 4 with u.dt2 store), then adjoint+imaging (4),
+    # 8 time steps in 2 checkpoint segments: forward (4 on the ring + 4 in history mode), then adjoint+imaging (4),
     # recompute (4), adjoint+imaging (4) -- every TMA kernel variant of the 3-D shot gradient
-    rec, cw, _ = solver.forward(save='checkpoint', time_M=8)
+    rec, cw, _ = solver.forward(save='checkpoint', time_M=8, segment=4, keep_segments=1)
     res = b.Receiver(name='res', grid=geom.model.grid, time_range=geom.time_axis, coordinates=geom.rec_positions)
     res._sdata.adopt_dev(rec._sdata.dev().clone())
     solver.gradient(rec=res, u=cw, time_M=8)

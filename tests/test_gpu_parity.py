@@ -143,24 +143,40 @@ def test_forward_gradient_3d(so, shape):
     eg = rel_l2(grad.data, g64)
     print("3-D so=%d gradient rel-L2 %.2e" % (so, eg))
     assert eg <= TOL_GRAD
-    # checkpoint + recompute must reproduce the full-history gradient bit for bit
-    # (default keep_segments=1: every segment but the last is restored and recomputed; 'auto': as many u.dt2
-    # segments as fit in HBM are kept from pass 1 - on this small grid all of them)
-    grad_c, _ = solver.gradient(rec=residual, u=None, checkpointing=True, segment=7)
-    assert np.array_equal(grad_c.data, grad.data)
+    # checkpoint + recompute: imaging by parts from ONE stored wavefield value per point (B2FWI_HIST_UVDT2,
+    # checkpoint.py) - equal to the full-history gradient up to fp32 rounding, and bitwise independent of the
+    # segmentation (segment length, how many trailing steps keep their wavefield from pass 1)
+    grad_c, _ = solver.gradient(rec=residual, u=None, checkpointing=True, segment=7, keep_segments=1)
+    ec, ec64 = rel_l2(grad_c.data, grad.data), rel_l2(grad_c.data, g64)
+    print("3-D so=%d checkpointed gradient vs full history %.2e, vs fp64 oracle %.2e" % (so, ec, ec64))
+    assert ec <= 5e-6 and ec64 <= TOL_GRAD
     grad_c2, _ = solver.gradient(rec=residual, u=None, checkpointing=True, keep_segments='auto')
-    assert np.array_equal(grad_c2.data, grad.data)
+    assert np.array_equal(grad_c2.data, grad_c.data)
     # forward(save='checkpoint') records the same data / illumination and hands its checkpoints to gradient()
     il_full = b.Function(name='il', grid=model.grid)
     solver.forward(save=True, illum=il_full)
     il_ck = b.Function(name='il', grid=model.grid)
     d_ck, cw, _ = solver.forward(save='checkpoint', illum=il_ck, segment=5, keep_segments=2)
-    assert cw.nkeep == 2 and len(cw.segs) > 3
+    assert cw.nkeep_steps == 10 and len(cw.segs) > 3
     assert np.array_equal(d_ck.data, d.data)
     assert np.array_equal(il_ck.data, il_full.data)
     assert rel_l2(il_full.data, np.sum(u64 ** 2, axis=0)) <= TOL_GRAD
     grad_c3, _ = solver.gradient(rec=residual, u=cw)
-    assert np.array_equal(grad_c3.data, grad.data)
+    assert np.array_equal(grad_c3.data, grad_c.data)
+    # a caller-supplied adjoint state is an initial condition (wavesolver.py:153-205): the boundary term of the
+    # summation by parts is then not zero and is added explicitly
+    rng = np.random.default_rng(3)
+    v0 = (1e-1 * rng.standard_normal((3,) + model.grid.shape)).astype(np.float32)
+    va = b.TimeFunction(name='v', grid=model.grid, time_order=2, space_order=so)
+    va.data[:] = v0
+    ga, _ = solver.gradient(rec=residual, u=u, v=va)
+    vb = b.TimeFunction(name='v', grid=model.grid, time_order=2, space_order=so)
+    vb.data[:] = v0
+    gb, _ = solver.gradient(rec=residual, u=None, v=vb, checkpointing=True, segment=6, keep_segments=1)
+    ev = rel_l2(gb.data, ga.data)
+    print("3-D so=%d checkpointed gradient with an initial adjoint state vs full history %.2e" % (so, ev))
+    assert ev <= 2e-5 and rel_l2(ga.data, grad.data) > 1e-3
+    assert rel_l2(vb.data, va.data) <= 1e-6
 
 
 def test_circle_fwi_kat_on_gpu():
@@ -325,7 +341,8 @@ def test_born_adjoint_and_linearisation(ndim):
 
 def test_fwi_objective_with_checkpointing_2d():
     """fwi_obj_single through the per-shot streaming engine: the checkpointed branch (taken automatically when the
-    saved history would not fit in HBM) must reproduce the saved-history objective, gradient and illumination."""
+    saved history would not fit in HBM) must reproduce the saved-history objective, residual and illumination bit for
+    bit, and the gradient up to the fp32 rounding of the imaging sum taken by parts (checkpoint.py)."""
     b = _b()
     from devito_fwi_b200 import configs, fwi
     g_true, g_init, g_const, _ = configs.marmousi(nsrc=3, tn=1500.)
@@ -342,7 +359,10 @@ def test_fwi_objective_with_checkpointing_2d():
         fwi.ENGINE = 'auto'
         fwi.CHECKPOINT = None
     assert f0 == f1 and np.array_equal(np.asarray(r0), np.asarray(r1))
-    assert np.array_equal(g0, g1) and np.array_equal(i0, i1)
+    assert np.array_equal(i0, i1)
+    eg = rel_l2(g1, g0)
+    print("2-D checkpointed (imaging by parts) vs saved-history gradient rel-L2 %.2e" % eg)
+    assert eg <= 5e-6
     assert np.abs(g0).max() > 0 and np.abs(i0).max() > 0
 
 
@@ -394,9 +414,12 @@ def test_forward_gradient_3d_tiles_inside_undamped_box(so, shape, nbl):
     print("3-D in-box so=%d %s nbl=%d (padded %s, nt=%d): traces %.2e wavefield %.2e gradient %.2e"
           % (so, shape, nbl, model.grid.shape, nt, e, eu, eg))
     assert e <= TOL_TRACE and eu <= TOL_TRACE and eg <= TOL_GRAD
-    # checkpointed gradient (u.dt2 imaging kernel, IMG = 2) == saved-history gradient, bit for bit
-    grad_c, _ = solver.gradient(rec=residual, u=None, checkpointing=True, segment=9)
-    assert np.array_equal(grad_c.data, grad.data)
+    # checkpointed gradient (imaging by parts from one stored wavefield value, TMA kernel IMG = 3): equal to the
+    # saved-history gradient up to fp32 rounding, to the fp64 oracle within the gradient tolerance
+    grad_c, _ = solver.gradient(rec=residual, u=None, checkpointing=True, segment=9, keep_segments=1)
+    ec, ec64 = rel_l2(grad_c.data, grad.data), rel_l2(grad_c.data, g64)
+    print("   checkpointed gradient vs saved history %.2e, vs fp64 oracle %.2e" % (ec, ec64))
+    assert ec <= 5e-6 and ec64 <= TOL_GRAD
     # same sweeps on the register-staged kernels (no TMA, c1 always loaded): shared point_update() => bitwise equal
     from devito_fwi_b200 import _lib
     old = _lib.lib().b2fwi_set_option(b"tma", 0)
@@ -462,3 +485,19 @@ def test_592_cubed_sweeps_vs_fp32_oracle():
     ev = rel_l2(v.data[0 % 3], vo[0 % 3])
     print("592^3 adjoint+imaging: gradient %.2e adjoint field %.2e" % (eg, ev))
     assert eg <= TOL_GRAD and ev <= TOL_TRACE
+    # the checkpointed gradient at full size (TMA adjoint kernel with imaging by parts, IMG = 3, in-box c1 skip, every
+    # plane chunk) against the saved-history imaging kernel just checked against the oracle: same source-driven
+    # forward wavefield, the same non-zero adjoint state (=> the boundary term of the summation by parts is exercised)
+    del uo, go, u
+    d2, u2, _ = solver.forward(save=True)
+    res.data[:] = d2.data
+    va = b.TimeFunction(name='v', grid=model.grid, time_order=2, space_order=8)
+    va.data[(nt - 2) % 3], va.data[(nt - 1) % 3] = 1e-3 * v0, 1e-3 * v1
+    g_full, _ = solver.gradient(rec=res, u=u2, v=va)
+    del u2
+    vb = b.TimeFunction(name='v', grid=model.grid, time_order=2, space_order=8)
+    vb.data[(nt - 2) % 3], vb.data[(nt - 1) % 3] = 1e-3 * v0, 1e-3 * v1
+    g_ck, _ = solver.gradient(rec=res, u=None, v=vb, checkpointing=True, segment=2, keep_segments=1)
+    ec = rel_l2(g_ck.data, g_full.data)
+    print("592^3 checkpointed gradient (imaging by parts) vs saved history: %.2e" % ec)
+    assert ec <= 2e-5 and np.abs(g_full.data).max() > 0

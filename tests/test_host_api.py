@@ -134,3 +134,27 @@ def test_checkpoint_segment_plan():
     assert S == 38 and len(segs) == 19                                             # ~sqrt(2 * 688)
     assert plan_segments(5, 4) == [] and plan_segments(3, 3) == [(3, 3)]
     assert plan_segments(1, 10, segment=4) == [(1, 4), (5, 8), (9, 10)]
+
+
+def test_checkpoint_keep_plan():
+    """How many trailing steps keep their wavefield from pass 1 for a given amount of spare HBM (checkpoint.plan_keep)."""
+    import math
+    from devito_fwi_b200.checkpoint import plan_keep
+
+    def need(steps, K, S, reserve=8):
+        rest = steps - K
+        return K + 2 + (S + 2 if rest > 0 else 0) + 2 * int(math.ceil(rest / float(S))) + reserve
+
+    # everything fits: the whole history is kept, nothing is recomputed
+    K, S = plan_keep(100, 1000)
+    assert K == 100
+    # the 592^3, nt=690 shot on a 180 GB B200: ~175 slices of 0.83 GB are spare
+    K, S = plan_keep(688, 175)
+    assert 80 <= K <= 120 and need(688, K, S) <= 175 and need(688, K + 1, S) > 175
+    # tight memory: no room for a pass-1 history, the plan is the plain two-level scheme
+    K, S = plan_keep(688, 60)
+    assert K == 0 or need(688, K, S) <= 60
+    # a fixed segment length is honoured
+    K, S = plan_keep(50, 40, segment=5)
+    assert S == 5 and need(50, K, 5) <= 40 and need(50, K + 1, 5) > 40
+    assert plan_keep(0, 100)[0] == 0
