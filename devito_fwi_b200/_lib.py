@@ -38,7 +38,12 @@ class Sparse(ctypes.Structure):
                 ("corner_off", ctypes.c_void_p), ("corner_w", ctypes.c_void_p),
                 ("ncell", ctypes.c_int32),
                 ("cell_off", ctypes.c_void_p), ("cell_ptr", ctypes.c_void_p),
-                ("contrib_pt", ctypes.c_void_p), ("contrib_w", ctypes.c_void_p)]
+                ("contrib_pt", ctypes.c_void_p), ("contrib_w", ctypes.c_void_p),
+                ("row_tile", ctypes.c_int32),
+                ("con_rowptr", ctypes.c_void_p), ("con_off", ctypes.c_void_p), ("max_row_con", ctypes.c_int32),
+                ("pt_order", ctypes.c_void_p), ("pt_home", ctypes.c_void_p), ("pt_rowptr", ctypes.c_void_p),
+                ("z_min", ctypes.c_int32), ("z_max", ctypes.c_int32),
+                ("r_min", ctypes.c_int32), ("r_max", ctypes.c_int32), ("p_min", ctypes.c_int32), ("p_max", ctypes.c_int32)]
 
 
 def sources():

@@ -119,6 +119,11 @@ int b2fwi_set_option(const char *name, int32_t value)
         set_tma_mask(value);
         return old;
     }
+    if (strcmp(name, "fuse") == 0) {
+        const int old = get_fuse();
+        set_fuse(value);
+        return old;
+    }
     set_error("unknown option '%s'", name);
     return B2FWI_EINVAL;
 }
@@ -178,11 +183,18 @@ int b2fwi_forward(const b2fwi_grid *g, const float *vp, const float *coef, float
         a.out = un; a.cur = uc; a.prev = up;
         a.illum = illum;
         a.d2u = d2u_out ? d2u_out + (int64_t)(time - d2u_t0) * L.elems : nullptr;
+        // injection / interpolation inside the sweep kernel where it can take them (TMA sweeps with tables), else
+        // as their own launches after it
+        const bool tma = tma_step_supported(L, a, 0);
+        const bool f_inj = tma && nsrc > 0 && a.chunk <= 1024 && tma_fusable(L, src_map, 1), f_itp = tma && nrec > 0 && tma_fusable(L, rec_map, 2);
+        a.inj.row_tile = a.itp.row_tile = 0;
+        if (f_inj) { a.inj = *src_map; a.inj_vals = src + (int64_t)time * nsrc; a.vp = vp; a.dt = dt; }
+        if (f_itp) { a.itp = *rec_map; a.itp_out = rec + (int64_t)time * nrec; }
         if ((rc = launch_step(L, a, 0, st))) return rc;
-        if (nsrc > 0 &&
+        if (nsrc > 0 && !f_inj &&
             (rc = launch_inject(un, vp, dt, src + (int64_t)time * nsrc, src_map, a.d2u, uc, up, a.inv_dt2, st)))
             return rc;
-        if (nrec > 0 && (rc = launch_interp(uc, rec + (int64_t)time * nrec, rec_map, st))) return rc;
+        if (nrec > 0 && !f_itp && (rc = launch_interp(uc, rec + (int64_t)time * nrec, rec_map, st))) return rc;
     }
     if (illum && time_m <= time_M && time_M == nt - 2) {     // the call producing the last slice adds it
         const int64_t sl = save ? time_M + 1 : (time_M + 1) % 3;
@@ -232,12 +244,18 @@ static int backward(const b2fwi_grid *g, const float *vp, const float *coef, flo
             a.h0 = (img == B2FWI_HIST_U) ? h - L.elems : nullptr;
             a.h2 = (img == B2FWI_HIST_U) ? h + L.elems : nullptr;
         }
+        const bool tma = tma_step_supported(L, a, img);
+        const bool f_inj = tma && nrec > 0 && a.chunk <= 1024 && tma_fusable(L, rec_map, 1);
+        const bool f_itp = tma && srca && nsrc > 0 && tma_fusable(L, src_map, 2);
+        a.inj.row_tile = a.itp.row_tile = 0;
+        if (f_inj) { a.inj = *rec_map; a.inj_vals = rec + (int64_t)time * nrec; a.vp = vp; a.dt = dt; }
+        if (f_itp) { a.itp = *src_map; a.itp_out = srca + (int64_t)time * nsrc; }
         if ((rc = launch_step(L, a, img, st))) return rc;
-        if (nrec > 0 &&
+        if (nrec > 0 && !f_inj &&
             (rc = launch_inject(vn, vp, dt, rec + (int64_t)time * nrec, rec_map, nullptr, nullptr, nullptr, a.inv_dt2, st,
                                 a.hist_uv ? grad : nullptr, a.hist_uv ? a.h1 : nullptr)))
             return rc;
-        if (srca && nsrc > 0 && (rc = launch_interp(vc, srca + (int64_t)time * nsrc, src_map, st))) return rc;
+        if (srca && nsrc > 0 && !f_itp && (rc = launch_interp(vc, srca + (int64_t)time * nsrc, src_map, st))) return rc;
     }
     return 0;
 }

@@ -450,28 +450,19 @@ __global__ void inject_kernel(float *__restrict__ field, const float *__restrict
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ncell) return;
     const int64_t off = cell_off[i];
-    const float v = vp[off];
     const float f0 = field[off];
-    float f = f0;
-    for (int j = cell_ptr[i]; j < cell_ptr[i + 1]; j++)
-        f += contrib_w[j] * vals[contrib_pt[j]] * dt * dt * v * v;
+    const float f = inject_cell(f0, cell_ptr[i], cell_ptr[i + 1], contrib_w, contrib_pt, vals, dt, vp[off]);
     field[off] = f;
     if (d2u) d2u[off] = d2u_of(prev[off], cur[off], f, inv_dt2);
-    if (grad) grad[off] = __fmaf_rn(-hist[off], __fmul_rn(__fsub_rn(f, f0), inv_dt2), grad[off]);
+    if (grad) grad[off] = img_inject_fix(grad[off], hist[off], f, f0, inv_dt2);
 }
 
-// out[p] = sum_c w_c * field[c]  (operators.py:137,176)
 __global__ void interp_kernel(const float *__restrict__ field, float *__restrict__ out, int npoint, int ncorner,
                               const int64_t *__restrict__ corner_off, const float *__restrict__ corner_w)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npoint) return;
-    float sum = 0.f;
-    for (int c = 0; c < ncorner; c++) {
-        const int64_t off = corner_off[(int64_t)p * ncorner + c];
-        if (off >= 0) sum += corner_w[(int64_t)p * ncorner + c] * field[off];
-    }
-    out[p] = sum;
+    out[p] = interp_point(field, p, ncorner, corner_off, corner_w);
 }
 
 int launch_inject(float *field, const float *vp, float dt, const float *vals, const b2fwi_sparse *m,

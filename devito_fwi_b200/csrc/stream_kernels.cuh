@@ -24,6 +24,12 @@ struct StepArgs {
     float c0, c0_lo;       // centre weight as hi + lo: exactly -2*sum of the rounded side weights (see api.cu)
     float cp[B2FWI_MAX_R + 1], cr[B2FWI_MAX_R + 1], cz[B2FWI_MAX_R + 1];
     int chunk;             // planes per CTA along the streamed axis (3-D); <= 0: pick automatically
+    // ---- sparse operators fused into the TMA sweeps (stream_tma.cu, service warps); all nullable
+    b2fwi_sparse inj, itp;               // (by value) inj.row_tile != 0: inject `inj_vals` into `out`; itp.row_tile != 0: record `cur`
+    const float *inj_vals;               // [inj.npoint] time sample of every injected point
+    const float *vp;                     // injection scale dt^2 vp^2 (operators.py:134,221)
+    float dt;
+    float *itp_out;                      // [itp.npoint]
 };
 
 void fill_stencil_weights(const Layout &L, StepArgs *a);
@@ -31,6 +37,10 @@ int pick_chunk(const Layout &L);
 int launch_step(const Layout &L, StepArgs a, int img, cudaStream_t st);
 // TMA-staged 3-D sweeps: forward, adjoint + imaging from u.dt2 (stream_tma.cu)
 bool tma_step_supported(const Layout &L, const StepArgs &a, int img);
+// the sweep kernel can take this map's injection / interpolation on board (tables present, 3-D, TMA path)
+bool tma_fusable(const Layout &L, const b2fwi_sparse *m, int what);   // what: 1 injection, 2 interpolation
+void set_fuse(int mask);          // b2fwi_set_option("fuse", mask): 1 source injection, 2 interpolation, 4 any injection
+int get_fuse();
 int launch_step_tma(const Layout &L, const StepArgs &a, int img, cudaStream_t st);
 void tma_tile_shape(int R, int *tz, int *tr);
 bool tma_enabled(int img);

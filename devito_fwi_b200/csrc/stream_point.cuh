@@ -17,6 +17,39 @@ static __device__ __forceinline__ float d2u_of(float um, float uc, float up, flo
     return __fmul_rn(__fadd_rn(__fmaf_rn(-2.f, uc, um), up), inv_dt2);
 }
 
+// Sparse operators, one definition for the stand-alone kernels and the service warps of the TMA sweeps (same
+// operation order => the fused and the three-launch step are bitwise identical).
+// field[cell] += sum_j w_j * vals[pt_j] * dt^2 * vp[cell]^2, contributions in ascending point order
+// (operators.py:134,221: expr = src * s**2 / m evaluated at each corner's own vp).
+static __device__ __forceinline__ float inject_term(float w, float val, float dt, float v)
+{
+    return __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(w, val), dt), dt), v), v);
+}
+static __device__ __forceinline__ float inject_cell(float f, int j0, int j1, const float *__restrict__ contrib_w,
+                                                   const int32_t *__restrict__ contrib_pt,
+                                                   const float *__restrict__ vals, float dt, float v)
+{
+    for (int j = j0; j < j1; j++) f = __fadd_rn(f, inject_term(contrib_w[j], vals[contrib_pt[j]], dt, v));
+    return f;
+}
+// out[p] = sum_c w_c * field[c]  (operators.py:137,176)
+static __device__ __forceinline__ float interp_point(const float *__restrict__ field, int64_t p, int ncorner,
+                                                    const int64_t *__restrict__ corner_off,
+                                                    const float *__restrict__ corner_w)
+{
+    float sum = 0.f;
+    for (int c = 0; c < ncorner; c++) {
+        const int64_t off = corner_off[p * ncorner + c];
+        if (off >= 0) sum += corner_w[p * ncorner + c] * field[off];
+    }
+    return sum;
+}
+// imaging by parts: the sweep formed v.dt2 before the injection, the injected increment is added afterwards
+static __device__ __forceinline__ float img_inject_fix(float g, float hist, float f_new, float f_old, float inv_dt2)
+{
+    return __fmaf_rn(-hist, __fmul_rn(__fsub_rn(f_new, f_old), inv_dt2), g);
+}
+
 // Staged-tile accessors: a generic pointer (register-staged / cp.async kernels) or a 32-bit shared-window address.
 struct SAddr { uint32_t a; };
 static __device__ __forceinline__ float4 ldt(const float *p, int off) { return ld4(p + off); }

@@ -85,14 +85,23 @@ struct TmaCfg {
     // operand-ring stage of unroll slot j is the compile-time j % NPCC when the ring turns a whole, odd number of
     // times per group of NQ planes; otherwise stage and parity are carried in two registers
     static constexpr bool PCT = (NQ % NPCC == 0) && (((NQ / NPCC) & 1) == 1);
-    static constexpr int NCONS = TZQ * TR, NTHREADS = NCONS + 32;
+    // warps are allocated in groups of four: 16 (8) compute warps + the producer leave three warps that cost no
+    // registers. They are the SERVICE warps: receiver interpolation of the tile (from global memory, free running)
+    // and the staging of the injection terms of plane i (warp i % NSVC, stage i % NI) that the compute threads add
+    // to their result before they store it.
+    static constexpr int NSVC = 3, NI = 6, NE = (R <= 4) ? 8 : 4;          // NE = B2FWI max_row_con the kernel takes
+    static constexpr int NCONS = TZQ * TR, NTHREADS = NCONS + 32 + 32 * NSVC;
     static constexpr int BAR_OFF = NCUR * CUR_STRIDE + NPCC * PCC_BYTES;    // mbarriers (64 slots reserved)
     static constexpr int W_OFF = BAR_OFF + 64 * 8;                          // Laplacian weights, 32 floats
     static constexpr int TH_OFF = W_OFF + 32 * 4;                           // per-thread constants, uint4 each
-    static constexpr int SMEM = TH_OFF + NCONS * 16;
+    static constexpr int NMW = 32;                                          // plane-mask words: chunks of <= 1024 planes
+    static constexpr int IMASK_OFF = TH_OFF + NCONS * 16;                   // [NMW] bit i: plane i has injection cells in this tile's rows
+    static constexpr int ICNT_OFF = IMASK_OFF + NMW * 4;                    // [NI][TR] staged terms per row
+    static constexpr int IENT_OFF = ICNT_OFF + NI * TR * 4;                 // [NI][TR][NE] {term, z in tile}
+    static constexpr int SMEM = IENT_OFF + NI * TR * NE * 8;
     static_assert(R >= 1 && R <= 8, "stencil radius");
     static_assert(PL_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
-    static_assert(2 * NCUR + NPCC <= 64 && 2 + 3 * R <= 32, "barrier / weight slots");
+    static_assert(2 * NCUR + NPCC + 2 * NI + 1 <= 64 && 2 + 3 * R <= 32, "barrier / weight slots");
 };
 
 // IMG: 0 forward sweep (EXTRAS: illumination / u.dt2 store), 2 adjoint sweep + imaging from stored u.dt2,
@@ -114,6 +123,9 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
     const uint32_t full_c = smem_s + C::BAR_OFF;                          // [NCUR]
     const uint32_t empty = full_c + NCUR * 8;                             // [NCUR]
     const uint32_t full_p = empty + NCUR * 8;                             // [NPCC]
+    const uint32_t inj_full = full_p + NPCC * 8;                          // [NI] injection terms of a plane staged
+    const uint32_t inj_empty = inj_full + C::NI * 8;                      // [NI] ... and consumed by every compute warp
+    const uint32_t mask_bar = inj_empty + C::NI * 8;                      // plane mask written (one arrival per service warp)
 
     const int tid = threadIdx.x;
     const int ztile0 = blockIdx.x * TZ, r0 = blockIdx.y * TR;
@@ -127,12 +139,26 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
                              ztile0 >= __ldg(a.box + 4) && ztile0 + TZ <= __ldg(a.box + 5);
     const int blo_p = tile_in_box ? __ldg(a.box + 0) : 0, bhi_p = tile_in_box ? __ldg(a.box + 1) : 0;
 
+    // ---- fused sparse operators (tables in a.inj / a.itp; z range test only - no global loads on the CTA's start-up path)
+    const int nrt = (a.nr + TR - 1) / TR;
+    // (bounding box of the map's cells against this CTA's tile and chunk: a point source switches the injection path on
+    // in the one to eight CTAs it touches, a receiver carpet in the z tile it lies in)
+    const bool inj_on = a.inj.row_tile && a.inj.z_max >= ztile0 && a.inj.z_min < ztile0 + TZ &&
+                        a.inj.r_max >= r0 && a.inj.r_min < r0 + TR && a.inj.p_max >= p_begin && a.inj.p_min < p_end;
+    const bool itp_on = a.itp.row_tile && a.itp.z_max >= ztile0 && a.itp.z_min < ztile0 + TZ &&
+                        a.itp.r_max >= r0 && a.itp.r_min < r0 + TR && a.itp.p_max >= p_begin && a.itp.p_min < p_end;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NCUR; s++) {
             mbar_init(full_c + 8 * s, 1);
             mbar_init(empty + 8 * s, C::NCONS / 32);
         }
+#pragma unroll
+        for (int s = 0; s < C::NI; s++) {
+            mbar_init(inj_full + 8 * s, 1);
+            mbar_init(inj_empty + 8 * s, C::NCONS / 32);
+        }
+        mbar_init(mask_bar, C::NSVC);
 #pragma unroll
         for (int s = 0; s < NPCC; s++) mbar_init(full_p + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -155,6 +181,102 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
     }
     __syncthreads();
 
+    if (tid >= C::NCONS + 32) {
+        // ------------------------------------------------------------------ service warps
+        if (!inj_on && !itp_on) return;
+        const int lane = tid & 31, sw = (tid - C::NCONS - 32) >> 5;
+        const uint32_t imask_s = smem_s + C::IMASK_OFF, icnt_s = smem_s + C::ICNT_OFF, ient_s = smem_s + C::IENT_OFF;
+        if (inj_on) {
+            // Which planes of the chunk have injection cells in this tile's rows: one table lookup per plane while the
+            // pipeline fills (words dealt round-robin to the three warps, two words per warp in flight: one memory
+            // latency for a chunk of up to 192 planes). The compute warps test one bit per plane; only flagged planes go
+            // through the staging handshake (a source touches two planes of a chunk, a receiver carpet every few).
+            {
+                const int rhi = min(r0 + TR, a.nr);
+                for (int b = 32 * sw; b < n_it; b += 64 * C::NSVC) {
+                    const int i0 = b + lane, i1 = b + 32 * C::NSVC + lane;
+                    int a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+                    if (i0 < n_it) {
+                        const int64_t row = (int64_t)(p_begin + i0) * a.nr;
+                        a0 = __ldg(a.inj.con_rowptr + row + r0); b0 = __ldg(a.inj.con_rowptr + row + rhi);
+                    }
+                    if (i1 < n_it) {
+                        const int64_t row = (int64_t)(p_begin + i1) * a.nr;
+                        a1 = __ldg(a.inj.con_rowptr + row + r0); b1 = __ldg(a.inj.con_rowptr + row + rhi);
+                    }
+                    const uint32_t w0 = __ballot_sync(0xffffffffu, b0 > a0), w1 = __ballot_sync(0xffffffffu, b1 > a1);
+                    if (lane == 0) {
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(imask_s + (uint32_t)(b >> 5) * 4u), "r"(w0) : "memory");
+                        if (b + 32 * C::NSVC < n_it)
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(imask_s + (uint32_t)((b >> 5) + C::NSVC) * 4u), "r"(w1) : "memory");
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(mask_bar);
+            }
+            mbar_wait(mask_bar, 0);
+            // k-th flagged plane -> warp k % NSVC, stage k % NI: one lane per row of the tile stages the row's terms in
+            // ascending (cell, point) order for the compute thread that owns the cell
+            int k = 0;
+            for (int b = 0; b < n_it; b += 32) {
+                uint32_t word;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(word) : "r"(imask_s + (uint32_t)(b >> 5) * 4u));
+                for (; word; word &= word - 1, k++) {
+                    if (k % C::NSVC != sw) continue;
+                    const int p = p_begin + b + __ffs(word) - 1, si = k % C::NI, row = r0 + lane;
+                    const int64_t plane0 = (int64_t)p * a.sp;
+                    int j0 = 0, j1 = 0;
+                    if (lane < TR && row < a.nr) {
+                        j0 = __ldg(a.inj.con_rowptr + (int64_t)p * a.nr + row);
+                        j1 = __ldg(a.inj.con_rowptr + (int64_t)p * a.nr + row + 1);
+                    }
+                    if (k >= C::NI) mbar_wait(inj_empty + 8 * si, (uint32_t)(k / C::NI - 1) & 1u);    // stage consumed (flagged plane k - NI)
+                    int cnt = 0;
+                    for (int j = j0; j < j1; j++) {
+                        const int64_t off = __ldg(a.inj.con_off + j);
+                        const int z = (int)((uint32_t)(off - plane0) % (uint32_t)a.sr) - ztile0;
+                        if (z >= 0 && z < TZ && cnt < C::NE) {
+                            const float term = inject_term(__ldg(a.inj.contrib_w + j), __ldg(a.inj_vals + __ldg(a.inj.contrib_pt + j)),
+                                                           a.dt, __ldg(a.vp + off));
+                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ient_s + (uint32_t)(((si * TR + lane) * C::NE + cnt) * 8)),
+                                         "r"(__float_as_uint(term)), "r"((uint32_t)z) : "memory");
+                            cnt++;
+                        }
+                    }
+                    if (lane < TR) asm volatile("st.shared.b32 [%0], %1;" ::"r"(icnt_s + (uint32_t)((si * TR + lane) * 4)), "r"(cnt) : "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(inj_full + 8 * si);
+                }
+            }
+        }
+        // receivers whose home cell lies in this tile: rec[t][pt] = interpolate(u[t]). Reads `cur` from global memory
+        // only (complete before the launch), so it needs no synchronisation with the sweep: lane <-> plane for the table
+        // lookup, then the warp walks the (few) points of each plane that has any.
+        if (itp_on) {
+            for (int b = 32 * sw; b < n_it; b += 32 * C::NSVC) {
+                const int i = b + lane;
+                int lo = 0, hi = 0;
+                if (i < n_it) {
+                    const int key = (p_begin + i) * nrt + (int)blockIdx.y;
+                    lo = __ldg(a.itp.pt_rowptr + key);
+                    hi = __ldg(a.itp.pt_rowptr + key + 1);
+                }
+                for (uint32_t m = __ballot_sync(0xffffffffu, hi > lo); m; m &= m - 1) {
+                    const int src_lane = __ffs(m) - 1;
+                    const int plo = __shfl_sync(0xffffffffu, lo, src_lane), phi = __shfl_sync(0xffffffffu, hi, src_lane);
+                    const int64_t plane0 = (int64_t)(p_begin + b + src_lane) * a.sp;
+                    for (int q = plo + lane; q < phi; q += 32) {
+                        const int z = (int)((uint32_t)(__ldg(a.itp.pt_home + q) - plane0) % (uint32_t)a.sr);
+                        if (z >= ztile0 && z < ztile0 + TZ) {
+                            const int pt = __ldg(a.itp.pt_order + q);
+                            a.itp_out[pt] = interp_point(a.cur, pt, a.itp.ncorner, a.itp.corner_off, a.itp.corner_w);
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
     if (tid >= C::NCONS) {
         // ------------------------------------------------------------------ producer (one lane)
         if (tid == C::NCONS) {
@@ -208,6 +330,9 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
         }
     }
     const uint32_t bar_fc = bars, bar_em = bars + NCUR * 8, bar_fp = bars + 2 * NCUR * 8;
+    const uint32_t bar_if = bar_fp + NPCC * 8, bar_ie = bar_if + C::NI * 8;
+    uint32_t icur = 0, ipar = 0;     // injection stage of the next flagged plane as a byte offset into the row counts, and its parity
+    if (inj_on) mbar_wait(bar_ie + C::NI * 8, 0);         // the plane mask is there (written by the service warps while the pipeline filled)
     const int tz = tid % C::TZQ, tr = tid / C::TZQ;
     const bool active = (r0 + tr < a.nr) && (ztile0 + tz * 4 < a.nz);
     const bool lane0 = (tid & 31) == 0;
@@ -283,9 +408,40 @@ step3d_tma_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CU
                     // no z masking: beyond nz the TMA unit filled u[t], u[t-1] and c2 with zeros, so o == 0 there
                     o = point_update<R, 3, SW, false>(w, q, j, SAddr{ctr_s + (j % NCUR) * C::CUR_STRIDE}, prev, c1, c2, 4);
                 }
-                // stage j (u[t] plane i) and the operand stage are free again
+                bool inj_here = false;
+                if (inj_on) {        // CTA-uniform; one mask bit per plane
+                    uint32_t word;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(word) : "r"(smem_s + C::IMASK_OFF + (uint32_t)(i >> 5) * 4u));
+                    inj_here = (word >> (i & 31)) & 1u;
+                }
+                if (inj_here) {
+                    // injection terms of this plane, staged by a service warp (a row rarely has any)
+                    mbar_wait(bar_if + (icur >> 3), ipar);
+                    uint32_t n;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(n) : "r"(smem_s + C::ICNT_OFF + icur + 4u * (uint32_t)tr));
+                    for (uint32_t e = 0; e < n; e++) {
+                        uint32_t tb, zl;
+                        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(tb), "=r"(zl)
+                                     : "r"(smem_s + C::IENT_OFF + (icur * 2u + 8u * (uint32_t)tr) * C::NE + 8u * e));
+                        if ((int)(zl >> 2) == tz) {
+                            const float t = __uint_as_float(tb);
+                            if ((zl & 3u) == 0u) o.x = __fadd_rn(o.x, t);
+                            else if ((zl & 3u) == 1u) o.y = __fadd_rn(o.y, t);
+                            else if ((zl & 3u) == 2u) o.z = __fadd_rn(o.z, t);
+                            else o.w = __fadd_rn(o.w, t);
+                        }
+                    }
+                }
+                // stage j (u[t] plane i), the operand stage and the injection stage are free again
                 __syncwarp();
-                if (lane0) mbar_arrive(bar_em + 8 * (j % NCUR));
+                if (lane0) {
+                    mbar_arrive(bar_em + 8 * (j % NCUR));
+                    if (inj_here) mbar_arrive(bar_ie + (icur >> 3));
+                }
+                if (inj_here) {
+                    icur += 4u * TR;
+                    if (icur == 4u * TR * C::NI) { icur = 0; ipar ^= 1u; }
+                }
                 if (active) {
                     F4W(a.out)[idx] = o;
                     if (IMG == 2) F4W(a.grad)[idx] = img4(g4, h1, q[(j + R) % NQ]);
@@ -384,6 +540,24 @@ bool tma_step_supported(const Layout &L, const StepArgs &a, int img)
     return (al & 15) == 0 && (L.sr % 4) == 0 && encode_fn() != nullptr;
 }
 
+// B2FWI_FUSE / b2fwi_set_option("fuse", 0|1): sparse operators inside the sweep kernels (default) or as separate launches
+// bit 0: injection of small maps (sources: <= FUSE_SMALL cells), bit 1: interpolation, bit 2: injection of any map.
+// Default 7 (everything inside the sweep), from interleaved runs on one box (592^3 so=8, 688 steps, 16384 receivers):
+// forward sweep with source injection + receiver interpolation 0.422 s fused against 0.428 s as three launches per
+// step; recompute + adjoint with the residual injection of the receiver carpet 1.057 s either way (the tiles of the
+// receivers' z range test the plane mask and go through the staging handshake, which costs about what the 6 us
+// kernel and its launch gap did). Only the CTAs inside the bounding box of a map's cells take part at all.
+static int g_fuse = []() { const char *e = getenv("B2FWI_FUSE"); return e ? (atoi(e) & 7) : 7; }();
+static const int FUSE_SMALL = 64;
+void set_fuse(int mask) { g_fuse = mask & 7; }
+int get_fuse() { return g_fuse; }
+bool tma_fusable(const Layout &L, const b2fwi_sparse *m, int what)
+{
+    const bool want = (what == 2) ? (g_fuse & 2) : ((g_fuse & 4) || ((g_fuse & 1) && m && m->ncell <= FUSE_SMALL));
+    return want && m && m->row_tile == 16 && m->con_rowptr && m->con_off && m->pt_order && m->pt_home &&
+           m->pt_rowptr && m->max_row_con <= (L.R <= 4 ? 8 : 4) && L.ndim == 3 && L.halo == 0;
+}
+
 // tile of the TMA kernels (pick_chunk sizes the plane chunks for whole waves of one CTA per SM)
 void tma_tile_shape(int R, int *tz, int *tr)
 {
@@ -396,7 +570,9 @@ bool tma_enabled(int img) { return (g_tma & (img == 0 ? 1 : 2)) != 0 && encode_f
 template <int R, int NPCC>
 static int launch_tma_r(const StepArgs &a, int img, cudaStream_t st)
 {
-    if (img == 2) return a.hist_uv ? launch_tma<R, NPCC, 3, false>(a, st) : launch_tma<R, NPCC, 2, false>(a, st);
+    // (so = 4: the 5-stage operand ring of the forward sweep does not fit next to a fourth operand array)
+    constexpr int NPI = (R == 2) ? 3 : NPCC;
+    if (img == 2) return a.hist_uv ? launch_tma<R, NPI, 3, false>(a, st) : launch_tma<R, NPI, 2, false>(a, st);
     return (a.illum || a.d2u) ? launch_tma<R, NPCC, 0, true>(a, st) : launch_tma<R, NPCC, 0, false>(a, st);
 }
 

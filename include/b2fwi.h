@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B2FWI_VERSION 100
+#define B2FWI_VERSION 101
 
 #define B2FWI_OK 0
 #define B2FWI_EINVAL (-1)   /* bad argument (shape, order, time range, null pointer) */
@@ -65,6 +65,20 @@ typedef struct b2fwi_sparse {
     const int32_t *cell_ptr;    /* [ncell+1] CSR row pointers into contrib_* */
     const int32_t *contrib_pt;  /* [ncontrib] point index, ascending within a cell */
     const float *contrib_w;     /* [ncontrib] multilinear weight */
+    /* Optional (3-D, halo 0): tables that let the TMA sweep kernels do injection and interpolation THEMSELVES
+     * (operators.py:131-140 is one operator; without them a step is three launches). Contributions are sorted
+     * by cell offset, i.e. by (plane, row, z), then by point. NULL / 0: injection and interpolation run as their
+     * own small kernels after each sweep. */
+    int32_t row_tile;           /* rows per row tile of the pt_* tables (16 = the TMA tile height), 0 = no tables */
+    const int32_t *con_rowptr;  /* [np*nr+1] first contribution whose cell lies in (plane, row) */
+    const int64_t *con_off;     /* [ncontrib] cell offset of every contribution (cell_off repeated) */
+    int32_t max_row_con;        /* most contributions any (plane, row) receives (the kernels stage <= 8, or <= 4 for so > 8) */
+    const int32_t *pt_order;    /* [npoint] points sorted by the offset of their first in-grid corner ("home") */
+    const int64_t *pt_home;     /* [npoint] that offset, ascending */
+    const int32_t *pt_rowptr;   /* [np*nrt+1] first entry of pt_order whose home lies in row tile (plane, rt); nrt = ceil(nr/row_tile) */
+    int32_t z_min, z_max;       /* index range of the cells (and homes) per dimension: tiles outside the box have no */
+    int32_t r_min, r_max;       /*   sparse work and pay nothing for the fusion (a point source touches 2 x 2 x 2 cells) */
+    int32_t p_min, p_max;
 } b2fwi_sparse;
 
 /* How the forward wavefield is supplied to the imaging condition of b2fwi_gradient(). */
@@ -85,7 +99,11 @@ const char *b2fwi_last_error(void);
 int64_t b2fwi_launch_count(void);
 /* Engine switches for A/B runs and the parity tests (process-wide; not thread-safe against running sweeps).
  *   "tma": bit 0 = TMA-staged forward sweep, bit 1 = TMA-staged adjoint + imaging sweep (default 3; 0 = the
- *          register-staged kernels everywhere). Returns the previous value (>= 0) or B2FWI_EINVAL. */
+ *          register-staged kernels everywhere).
+ *   "fuse": sparse operators inside the TMA sweep kernels (service warps) instead of separate launches after each
+ *          sweep; bit 0 = injection of small maps (sources), bit 1 = interpolation, bit 2 = injection of any map
+ *          (default 7; 0 = three launches per step). Needs the optional tables of b2fwi_sparse.
+ *   Returns the previous value (>= 0) or B2FWI_EINVAL. */
 int b2fwi_set_option(const char *name, int32_t value);
 
 /* Layout of one haloed slice: element strides per dimension, offset of domain cell (0,..,0), total floats. */

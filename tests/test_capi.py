@@ -28,7 +28,7 @@ def test_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), "missing export %s" % name
     assert declared == set(_lib.PROTOTYPES), "ctypes prototypes out of sync with the header"
-    assert lib.b2fwi_version() == 100
+    assert lib.b2fwi_version() == 101
 
 
 @pytest.mark.parametrize("shape", [(380, 186), (281, 281), (75, 67), (592, 592, 592), (34, 29, 38)])

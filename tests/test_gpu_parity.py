@@ -433,6 +433,33 @@ def test_forward_gradient_3d_tiles_inside_undamped_box(so, shape, nbl):
     assert np.array_equal(d2.data, d.data)
     assert np.array_equal(u2.data[nt - 1], u.data[nt - 1])
     assert np.array_equal(grad2.data, grad.data)
+    # sparse operators inside the sweep kernels (service warps) vs as separate launches. "fuse" mask: 1 = injection of
+    # small maps (sources), 2 = interpolation, 4 = injection of any map; default 7 = everything (above), 0 = nothing.
+    # Forward records, the adjoint field and its source-side record are bitwise equal, with two launches fewer per
+    # step; the checkpointed gradient differs by rounding at the injected cells only (the fused sweep images with the
+    # injected v[t-1] directly, the separate injection kernel adds that part of the by-parts product afterwards)
+    lib = _lib.lib()
+    res = {}
+    for mask in (7, 0):
+        old = lib.b2fwi_set_option(b"fuse", mask)
+        try:
+            sv = b.AcousticWaveSolver(model, geom, space_order=so)
+            dm, _, _ = sv.forward()
+            gm, _ = sv.gradient(rec=residual, u=None, checkpointing=True, segment=9, keep_segments=1)
+            n0 = lib.b2fwi_launch_count()
+            sm, vm, _ = sv.adjoint(rec=residual)
+            res[mask] = (np.array(dm.data), np.array(gm.data), np.array(sm.data), np.array(vm.data),
+                         lib.b2fwi_launch_count() - n0)
+        finally:
+            lib.b2fwi_set_option(b"fuse", old)
+    assert old == 7
+    for mask in (7, 0):
+        assert np.array_equal(res[mask][0], d.data)
+        assert rel_l2(res[mask][1], grad_c.data) <= 1e-6
+    assert np.array_equal(res[7][2], res[0][2]) and np.array_equal(res[7][3], res[0][3])
+    assert np.abs(res[7][2]).max() > 0
+    print("   launches per adjoint sweep: fused %d, separate %d (%d steps)" % (res[7][4], res[0][4], nt - 2))
+    assert res[0][4] - res[7][4] == 2 * (nt - 2) and res[7][4] < nt + 8
 
 
 def test_592_cubed_sweeps_vs_fp32_oracle():

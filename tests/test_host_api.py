@@ -158,3 +158,51 @@ def test_checkpoint_keep_plan():
     K, S = plan_keep(50, 40, segment=5)
     assert S == 5 and need(50, K, 5) <= 40 and need(50, K + 1, 5) > 40
     assert plan_keep(0, 100)[0] == 0
+
+
+def test_sparse_fuse_tables():
+    """Bucketing of injection contributions by (plane, row) and of recorded points by (plane, 16-row tile) for the
+    sweep kernels' service warps."""
+    import devito_fwi_b200 as b
+    from devito_fwi_b200 import sparse
+    shape = (20, 37, 50)
+    model = b.Model(origin=(0., 0., 0.), spacing=(10., 10., 10.), shape=shape, space_order=4,
+                    vp=np.full(shape, 2.0, np.float32), nbl=3, bcs="damp")
+    grid = model.grid
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(5., 10. * np.array(shape) - 5., size=(60, 3))
+    off, w = sparse.resolve(grid, pts)
+    flat, pt = off.ravel(), np.repeat(np.arange(60), 8)
+    order = np.lexsort((pt, flat))
+    v_off = flat[order]
+    cells, start = np.unique(v_off, return_index=True)
+    cell_ptr = np.append(start, v_off.size).astype(np.int32)
+    t, max_row_con = sparse.fuse_tables(grid, off, cells, cell_ptr)
+    npl, nr = grid.shape[0], grid.shape[1]
+    sr = grid.slice_shape[2]
+    sp = grid.slice_shape[1] * sr
+    nrt = (nr + 15) // 16
+    assert np.array_equal(t['con_off'], v_off)
+    assert t['con_rowptr'].shape == (npl * nr + 1,) and t['con_rowptr'][0] == 0 and t['con_rowptr'][-1] == v_off.size
+    assert max_row_con == np.diff(t['con_rowptr']).max() and 0 < max_row_con <= sparse.MAX_ROW_CON
+    for k in rng.integers(0, npl * nr, 80):
+        p, r = divmod(int(k), nr)
+        c = t['con_off'][t['con_rowptr'][k]:t['con_rowptr'][k + 1]]
+        assert np.all(c // sp == p) and np.all((c % sp) // sr == r)
+    # every point appears once, filed under its first in-grid corner, bucketed by (plane, 16-row tile)
+    assert sorted(t['pt_order'].tolist()) == list(range(60))
+    assert np.all(np.diff(t['pt_home']) >= 0) and t['pt_rowptr'][-1] == 60 and t['pt_rowptr'].shape == (npl * nrt + 1,)
+    for k in rng.integers(0, npl * nrt, 60):
+        p, rt = divmod(int(k), nrt)
+        h = t['pt_home'][t['pt_rowptr'][k]:t['pt_rowptr'][k + 1]]
+        assert np.all(h // sp == p) and np.all((h % sp) // sr // 16 == rt)
+    for i in (0, 37, 59):
+        assert t['pt_home'][i] == off[t['pt_order'][i]][0]
+    # maps that the service warps do not take run as separate kernels: too dense, or a point outside the grid
+    dense = np.stack(np.meshgrid(np.arange(0., 190., 2.5), np.arange(0., 360., 2.5), [25.], indexing='ij'), -1).reshape(-1, 3)
+    off2, _ = sparse.resolve(grid, dense)
+    f2 = np.sort(off2.ravel())
+    c2, s2 = np.unique(f2, return_index=True)
+    assert sparse.fuse_tables(grid, off2, c2, np.append(s2, f2.size).astype(np.int32)) == ({}, 0)
+    off3, _ = sparse.resolve(grid, np.array([[-500., 10., 10.]]))
+    assert (off3 < 0).all() and sparse.fuse_tables(grid, off3, np.zeros(0, np.int64), np.zeros(1, np.int32)) == ({}, 0)
