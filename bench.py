@@ -436,7 +436,7 @@ def layered3d(args, world, rank, local, lib, headline):
         for r in obs.values():
             r._sdata.dev()
         if warm:
-            sv.objective(obs, host=False)                    # warm-up (allocations of ~70 GB of checkpoints / u.dt2)
+            sv.objective(obs, host=False)                    # warm-up (allocations of ~150 GB of checkpoints / kept wavefield)
 
         def timed(host):
             if world > 1:
@@ -488,9 +488,11 @@ def layered3d(args, world, rank, local, lib, headline):
             "ms_per_launch": round(s_fwd.time / steps * 1e3, 4),
             "shot_gradient": {"algorithmic_B_per_point_step": 52, "achieved": weak["algorithmic_GBs_52B"] / world,
                               "frac": weak["frac_of_measured_hbm_per_gpu"],
-                              "note": "forward(+checkpoints) + recompute(+u.dt2 store) + adjoint/imaging = 76 B per "
-                                      "point-step actually streamed for 52 algorithmic (the recompute sweep is the "
-                                      "price of checkpointing)"}}
+                              "note": "forward (18.7 B per point-step moved: c1 is not read inside the undamped box) + "
+                                      "recompute of the steps whose wavefield was not kept from pass 1 (18.7 B x ~85 %) + "
+                                      "adjoint with imaging by parts from ONE stored wavefield value (31 B) = ~66 B per "
+                                      "point-step actually streamed for 52 algorithmic; the recompute sweep is the price "
+                                      "of checkpointing (checkpoint.py)"}}
     out = {"workload": "layered3d (BASELINE.json configs[4]): 592^3 = 512^3 + 2*40, so=8, nt=%d (tn=%g), %d receivers, "
                        "L2 gradient with on-device checkpointing, streaming engine (TMA)" % (geom0.nt, args.tn3d, geom0.nrec),
            "weak_one_shot_per_gpu": weak, "strong_8_shots": strong, "roofline": roof, "hbm_peak_alloc_GB": hbm_gb}

@@ -51,6 +51,7 @@ int make_layout(const b2fwi_grid *g, Layout *L)
     L->ndim = g->ndim;
     L->halo = g->halo;
     L->R = R;
+    L->fs = g->fs ? 1 : 0;
     if (g->ndim == 2) {
         L->np = 1; L->nr = g->shape[0]; L->nz = g->shape[1];
         L->sr = ((int64_t)L->nz + 2 * H + 31) / 32 * 32;

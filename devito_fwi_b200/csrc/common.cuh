@@ -39,6 +39,7 @@ struct Layout {
     int64_t base;        // offset of domain cell (0,0,0)
     int64_t elems;       // floats per haloed slice
     int R;               // stencil radius
+    int fs;              // free surface at z index 0 (b2fwi_grid.fs)
     double inv_h2[3];    // 1/h^2 for plane, row, z directions
 };
 

@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(TZQ *TR, MINB) step_kernel(const __grid_consta
 
                 if (active) {
                     const float4 C = q[(j + QC) % NQ];
-                    const float4 o = point_update<R, NDIM, SW>(a, q, j, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, zvalid);
+                    const float4 o = point_update<R, NDIM, SW>(a, q, j, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, zvalid,
+                                                               (a.fs && z0 <= R) ? z0 : -1);
                     F4W(a.out)[idx] = o;
                     if (IMG == 1) F4W(a.grad)[idx] = img4(g4, d2u4(h0, h1, h2, a.inv_dt2), C);
                     if (IMG == 2) F4W(a.grad)[idx] = img4(g4, h1, a.hist_uv ? d2u4(prev, C, o, a.inv_dt2) : C);
@@ -299,7 +300,8 @@ __global__ void __launch_bounds__(256, 2) step3d_async_kernel(const __grid_const
             const float4 *ax = aux + (slot * NAUX) * 256 + tid;
             const float4 prev = ax[0], c1 = ax[256], c2 = ax[512];
             const float4 C = q[QC];
-            const float4 o = point_update<R, 3, SW>(a, q, 0, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, zvalid);
+            const float4 o = point_update<R, 3, SW>(a, q, 0, tb + (R + tr) * SW + ZH + 4 * tz, prev, c1, c2, zvalid,
+                                                    (a.fs && z0 <= R) ? z0 : -1);
             st4(a.out + own0 + pofs, o);
             if (IMG == 2) st4(a.grad + own0 + pofs, img4(ax[768], ax[1024], a.hist_uv ? d2u4(prev, C, o, a.inv_dt2) : C));
             if (a.illum) st4(a.illum + own0 + pofs, fma4(C, C, il));
@@ -382,7 +384,7 @@ int pick_chunk(const Layout &L)
     if (L.ndim != 3) return 1;
     int tzc, trc, bps;
     tile_shape(L.ndim, &tzc, &trc, &bps);
-    if (L.halo == 0 && tma_enabled(0)) { tma_tile_shape(L.R, &tzc, &trc); bps = 1; }     // one TMA CTA per SM
+    if (L.halo == 0 && !L.fs && tma_enabled(0)) { tma_tile_shape(L.R, &tzc, &trc); bps = 1; }     // one TMA CTA per SM
     else if (L.R > 4) { tzc = 64; trc = 16; bps = 2; }
     static int sms = 0;
     if (sms == 0) {
@@ -414,7 +416,7 @@ static bool use_async(int R) { return g_async < 0 ? R > 4 : g_async == 1; }
 
 int launch_step(const Layout &L, StepArgs a, int img, cudaStream_t st)
 {
-    a.np = L.np; a.nr = L.nr; a.nz = L.nz; a.halo = L.halo; a.sp = L.sp; a.sr = L.sr;
+    a.np = L.np; a.nr = L.nr; a.nz = L.nz; a.halo = L.halo; a.sp = L.sp; a.sr = L.sr; a.fs = L.fs;
     if (a.chunk <= 0) a.chunk = pick_chunk(L);
     if (tma_step_supported(L, a, img)) return launch_step_tma(L, a, img, st);
     const int nchunks = (L.ndim == 3) ? (L.np + a.chunk - 1) / a.chunk : 1;

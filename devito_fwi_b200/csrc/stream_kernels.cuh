@@ -6,6 +6,7 @@ namespace b2fwi {
 
 struct StepArgs {
     int np, nr, nz, halo;
+    int fs;                // free surface at z = 0: mirrored z stencil in the top rows (stream_point.cuh)
     int64_t sp, sr;
     float *out;            // slice written: u[t+1] (forward) or v[t-1] (backward)
     const float *cur;      // u[t] / v[t]

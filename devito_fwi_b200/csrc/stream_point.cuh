@@ -69,8 +69,22 @@ static __device__ __forceinline__ float4 ldt(SAddr s, int off)
 //   MASKZ = false: the caller guarantees c2 == 0 and u == 0 beyond nz (TMA zero fill), which makes the update 0 there.
 // (split in two so that a kernel short of registers can fetch prev / c1 / c2 AFTER the Laplacian: point_laplacian +
 // point_finish is point_update, operation for operation)
+// Free surface (operators.py:8-35): in the top rows a reference u[z - k] becomes sign(z - k) * u[|z - k|] - the
+// antisymmetric mirror about index 0, whose own value counts as zero when it is reached through a negative offset.
+// zl[t] holds u at z = fsz - ZH + t (fsz: global z of the thread's quad, 0 / 4 / 8): positions <= 0 are rewritten.
+template <int F, int ZH>
+static __device__ __forceinline__ void mirror_top(float *zl)
+{
+    if (F <= ZH) {
+#pragma unroll
+        for (int t = 0; t < ZH - F; t++) zl[t] = -zl[2 * ZH - 2 * F - t];
+        zl[ZH - F] = 0.f;
+    }
+}
+
+// fsz: global z index of the quad when the model has a free surface and the quad is within reach of it (<= R), else -1
 template <int R, int NDIM, int SW, class W = StepArgs, class TP = const float *>
-static __device__ __forceinline__ float4 point_laplacian(const W &a, const float4 *q, int j, TP ctr)
+static __device__ __forceinline__ float4 point_laplacian(const W &a, const float4 *q, int j, TP ctr, int fsz = -1)
 {
     constexpr int RZ4 = (R + 3) / 4, ZH = 4 * RZ4;
     constexpr int NQ = (NDIM == 3) ? 2 * R + 1 : 1;
@@ -93,6 +107,11 @@ static __device__ __forceinline__ float4 point_laplacian(const W &a, const float
         zl[ZH + 4 + 4 * i + 2] = Rq.z; zl[ZH + 4 + 4 * i + 3] = Rq.w;
     }
     zl[ZH + 0] = C.x; zl[ZH + 1] = C.y; zl[ZH + 2] = C.z; zl[ZH + 3] = C.w;
+    if (fsz >= 0) {          // a few threads per row, and only in models with a free surface
+        if (fsz == 0) mirror_top<0, ZH>(zl);
+        else if (fsz == 4) mirror_top<4, ZH>(zl);
+        else mirror_top<8, ZH>(zl);
+    }
     // z direction in packed pairs. Even offsets k pair up naturally: (o0,o1) = (z[k],z[k+1]) + (z[-k],z[1-k]) are
     // aligned register pairs. For odd k those pairs straddle registers (two MOVs each), so the sums are formed
     // for the aligned output pairs (o-1,o0), (o1,o2), (o3,o4) instead - three packed adds, outer lanes unused -
@@ -139,11 +158,11 @@ static __device__ __forceinline__ float4 point_finish(float4 C, float4 lap, floa
 
 template <int R, int NDIM, int SW, bool MASKZ = true, class W = StepArgs, class TP = const float *>
 static __device__ __forceinline__ float4 point_update(const W &a, const float4 *q, int j, TP ctr,
-                                                     float4 prev, float4 c1, float4 c2, int zvalid)
+                                                     float4 prev, float4 c1, float4 c2, int zvalid, int fsz = -1)
 {
     constexpr int NQ = (NDIM == 3) ? 2 * R + 1 : 1;
     constexpr int QC = (NDIM == 3) ? R : 0;
-    const float4 lap = point_laplacian<R, NDIM, SW, W, TP>(a, q, j, ctr);
+    const float4 lap = point_laplacian<R, NDIM, SW, W, TP>(a, q, j, ctr, fsz);
     return point_finish<MASKZ>(q[(j + QC) % NQ], lap, prev, c1, c2, zvalid);
 }
 

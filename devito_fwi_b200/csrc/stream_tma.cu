@@ -532,6 +532,7 @@ int get_tma_mask() { return g_tma; }
 bool tma_step_supported(const Layout &L, const StepArgs &a, int img)
 {
     if (L.ndim != 3 || !(img == 0 || img == 2) || L.halo != 0 || L.R < 1 || L.R > 8) return false;
+    if (L.fs) return false;      // free-surface models run on the register-staged kernels (mirrored top rows, stream_point.cuh)
     if (!(g_tma & (img == 0 ? 1 : 2))) return false;
     if (img == 2 && (!a.h1 || !a.grad || (((uintptr_t)a.h1 | (uintptr_t)a.grad) & 15))) return false;
     if (img == 2 && (a.illum || a.d2u)) return false;

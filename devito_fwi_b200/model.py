@@ -74,8 +74,6 @@ class GenericModel(object):
 
     def __init__(self, origin, spacing, shape, space_order, nbl=20,
                  dtype=np.float32, subdomains=(), bcs="damp", grid=None, fs=False):
-        if fs:
-            raise NotImplementedError("free surface is outside the B200 hot path (SURVEY.md section 8f)")
         self.shape = tuple(shape)
         self.space_order = space_order
         self.nbl = int(nbl)
@@ -83,6 +81,11 @@ class GenericModel(object):
         self.fs = fs
         origin_pml = [dtype(o - s*nbl) for o, s in zip(origin, spacing)]
         shape_pml = np.array(shape) + 2 * self.nbl
+        if fs:
+            # free surface: no absorbing layer above index 0 of the last dimension (seismic/model.py:102-109); the
+            # top rows then use the mirrored stencil of operators.py:8-35 (grid.fs travels to the kernels)
+            origin_pml[-1] = dtype(origin[-1])
+            shape_pml[-1] -= self.nbl
         if grid is None:
             # physical extent is counted per cell, hence shape - 1 (seismic/model.py:113-117)
             extent = tuple(np.array(spacing) * (shape_pml - 1))
@@ -90,6 +93,7 @@ class GenericModel(object):
                              subdomains=subdomains)
         else:
             self.grid = grid
+        self.grid.fs = bool(fs)
         self._spacing = tuple(dtype(s) for s in spacing)
         self._physical_parameters = set()
         self.damp = None

@@ -277,7 +277,8 @@ class ResidentSurvey(object):
         else:
             self.plan = (choose_plan(self.grid, self.space_order, model.nbl, self.nshots, min_rows) if min_cluster == 1
                          else plan_model(self.grid, self.space_order, model.nbl, min_cluster, min_rows))
-        if self.plan is None or not self.supported(geometry, self.space_order):
+        if self.plan is None or not self.supported(geometry, self.space_order) or getattr(model, 'fs', False):
+            # (free-surface models: the mirrored top rows exist in the streaming kernels only)
             raise ValueError("model does not fit the SM-resident engine")
         self.nt = geometry.nt
         self.dt = float(geometry.dt)

@@ -48,6 +48,7 @@ def grid_struct(grid, space_order):
     g.ndim = grid.dim
     g.space_order = int(space_order)
     g.halo = HALO
+    g.fs = 1 if getattr(grid, 'fs', False) else 0
     for d in range(grid.dim):
         g.shape[d] = grid.shape[d]
         g.spacing[d] = float(grid.spacing[d])

@@ -47,6 +47,8 @@ typedef struct b2fwi_grid {
     int32_t halo;          /* zero cells around the domain in the device layout; multiple of 4, normally 0 */
     float spacing[3];      /* model.spacing */
     float origin[3];       /* padded origin, model.grid.origin (seismic/model.py:100) */
+    int32_t fs;            /* free surface at index 0 of the last dimension (Model(fs=True), model.py:102-109): the top
+                            * rows take the antisymmetric mirror stencil of operators.py:8-35. Streaming engine only. */
 } b2fwi_grid;
 
 /*

@@ -18,6 +18,7 @@
  *   seismic/inversion/fwi.py:95-97,121      objective 39113, grad min/max -821/2442, 5th GD objective 3828 (+-10)
  *   seismic/acoustic/acoustic_example.py:75-79  3-D |rec|_2 = 459.1678 (rtol 1e-3, fp64)
  *   seismic/acoustic/accuracy.ipynb cells 14,16 trace min/max -5.349877e-03/+8.529867e-03, RMS err 1.1265e-05
+ *   seismic/acoustic/acoustic_example.py:75-79  free surface, fp32: |rec|_2 = 369.955 (rtol 1e-3)
  * The named Marmousi / circle(so=6) / 3-D 512^3 shapes have no stored outputs in the
  * reference ("parity unpinned" at those shapes).
  *
@@ -48,6 +49,7 @@ typedef struct {
     int space_order; /* even, 2..16 */
     double spacing[3];
     double origin[3]; /* padded origin (model.py:100), already rounded through the grid dtype */
+    int fs;           /* free surface at index 0 of the last dimension (model.py:102-109, operators.py:8-35) */
 } oracle_grid;
 
 /*

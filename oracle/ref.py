@@ -29,7 +29,7 @@ _LIBS = {}
 class _Grid(ctypes.Structure):
     _fields_ = [("ndim", ctypes.c_int), ("shape", ctypes.c_int * 3),
                 ("space_order", ctypes.c_int), ("spacing", ctypes.c_double * 3),
-                ("origin", ctypes.c_double * 3)]
+                ("origin", ctypes.c_double * 3), ("fs", ctypes.c_int)]
 
 
 def build(fast=False):
@@ -56,13 +56,16 @@ def laplace_coeffs(space_order):
     return np.array(c[:space_order // 2 + 1])
 
 
-def pad_edge(vp, nbl):
-    """Edge-replicated padding."""
-    return np.pad(vp, [(nbl, nbl)] * vp.ndim, mode="edge")
+def pad_edge(vp, nbl, fs=False):
+    """Edge-replicated padding; with a free surface no layer above the last dimension (model.py:157)."""
+    pads = [(nbl, nbl)] * vp.ndim
+    if fs:
+        pads[-1] = (0, nbl)
+    return np.pad(vp, pads, mode="edge")
 
 
-def init_damp(shape_padded, nbl, spacing, abc_type="damp", dtype=np.float32):
-    """model.py:13-51: additive per-dimension sponge profile."""
+def init_damp(shape_padded, nbl, spacing, abc_type="damp", dtype=np.float32, fs=False):
+    """model.py:13-51: additive per-dimension sponge profile (no left layer in the last dimension under fs, :33)."""
     damp = np.full(shape_padded, 1.0 if abc_type == "mask" else 0.0, dtype=np.float64)
     if nbl == 0:
         return damp.astype(dtype)
@@ -74,7 +77,8 @@ def init_damp(shape_padded, nbl, spacing, abc_type="damp", dtype=np.float32):
         val = -val
     for d, h in enumerate(spacing):
         prof = np.zeros(shape_padded[d])
-        prof[:nbl] += val / h
+        if not (fs and d == len(spacing) - 1):
+            prof[:nbl] += val / h
         prof[-nbl:] += (val / h)[::-1]
         sh = [1] * len(shape_padded)
         sh[d] = shape_padded[d]
@@ -127,21 +131,26 @@ class RefModel(object):
     """Numpy stand-in for seismic.Model (model.py:227-400), acoustic fields only."""
 
     def __init__(self, origin, spacing, shape, space_order, vp, nbl=20, dtype=np.float32,
-                 dt=None):
+                 dt=None, fs=False):
         self.shape = tuple(shape)
         self.spacing = tuple(float(s) for s in spacing)
         self.space_order = int(space_order)
         self.nbl = int(nbl)
         self.dtype = dtype
         self.origin = tuple(dtype(o) for o in origin)
-        self.origin_pml = tuple(dtype(o - s * nbl) for o, s in zip(origin, spacing))
-        self.shape_pml = tuple(int(n) + 2 * self.nbl for n in shape)
+        self.fs = bool(fs)
+        origin_pml = [dtype(o - s * nbl) for o, s in zip(origin, spacing)]
+        shape_pml = [int(n) + 2 * self.nbl for n in shape]
+        if self.fs:                                  # model.py:102-109
+            origin_pml[-1] = dtype(origin[-1])
+            shape_pml[-1] -= self.nbl
+        self.origin_pml, self.shape_pml = tuple(origin_pml), tuple(shape_pml)
         self.dim = len(shape)
         self._dt = dt
         if np.isscalar(vp):
             vp = np.full(shape, vp)
-        self.vp = pad_edge(np.asarray(vp, dtype=dtype), self.nbl)
-        self.damp = init_damp(self.shape_pml, self.nbl, self.spacing, "damp", dtype)
+        self.vp = pad_edge(np.asarray(vp, dtype=dtype), self.nbl, self.fs)
+        self.damp = init_damp(self.shape_pml, self.nbl, self.spacing, "damp", dtype, self.fs)
 
     @property
     def domain_size(self):
@@ -154,7 +163,7 @@ class RefModel(object):
 
     def update_vp(self, vp):
         vp = np.asarray(vp, dtype=self.dtype)
-        self.vp = vp.copy() if vp.shape == self.shape_pml else pad_edge(vp, self.nbl)
+        self.vp = vp.copy() if vp.shape == self.shape_pml else pad_edge(vp, self.nbl, self.fs)
 
     def grid_struct(self, space_order=None):
         g = _Grid()
@@ -164,6 +173,7 @@ class RefModel(object):
             g.shape[d] = self.shape_pml[d]
             g.spacing[d] = self.spacing[d]
             g.origin[d] = float(self.origin_pml[d])
+        g.fs = int(self.fs)
         return g
 
 

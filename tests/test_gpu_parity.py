@@ -528,3 +528,79 @@ def test_592_cubed_sweeps_vs_fp32_oracle():
     ec = rel_l2(g_ck.data, g_full.data)
     print("592^3 checkpointed gradient (imaging by parts) vs saved history: %.2e" % ec)
     assert ec <= 2e-5 and np.abs(g_full.data).max() > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# Free surface (Model(fs=True); operators.py:8-35, model.py:102-109): streaming kernels vs the oracle, whose mirrored
+# stencil is pinned by the reference's own KAT (|rec| = 369.955, tests/test_oracle_kat.py)
+@pytest.mark.parametrize("so,shape", [(4, (61, 45)), (8, (50, 38)), (4, (30, 26, 34)), (8, (28, 24, 30)), (16, (26, 22, 40))])
+def test_free_surface_forward_gradient(so, shape):
+    b = _b()
+    nd = len(shape)
+    nbl = 10
+    vp = np.full(shape, 1.6, dtype=np.float32)
+    vp[..., shape[-1] // 2:] = 2.4
+    model = b.Model(origin=(0.,) * nd, spacing=(10.,) * nd, shape=shape, space_order=so, vp=vp, nbl=nbl, bcs="damp",
+                    fs=True)
+    assert model.grid.shape[-1] == shape[-1] + nbl and model.grid.shape[0] == shape[0] + 2 * nbl
+    assert float(model.grid.origin[-1]) == 0.0 and float(model.grid.origin[0]) == -100.0
+    ext = [10. * (n - 1) for n in shape]
+    src = np.array([[0.47 * e for e in ext[:-1]] + [12.3]])                 # shallow source: its ghost matters
+    if nd == 2:
+        rec = np.stack([np.linspace(8.1, ext[0] - 7.7, 23), np.full(23, 21.7)], axis=1)
+    else:
+        rx, ry = np.meshgrid(np.linspace(12.5, ext[0] - 9.9, 6), np.linspace(8.2, ext[1] - 8.1, 5), indexing='ij')
+        rec = np.stack([rx.ravel(), ry.ravel(), np.full(rx.size, 21.7)], axis=1)
+    geom = b.AcquisitionGeometry(model, rec, src, 0., 160., f0=0.02, src_type='Ricker')
+    solver = b.AcousticWaveSolver(model, geom, space_order=so)
+    d, u, _ = solver.forward(save=True)
+    nt, dt = geom.nt, float(geom.dt)
+    sl = tuple([slice(nbl, -nbl)] * (nd - 1) + [slice(0, -nbl)])
+    rm = ref.RefModel([0.] * nd, [10.] * nd, shape, so, np.array(model.vp.data)[sl].astype(np.float64), nbl=nbl,
+                      dtype=np.float64, dt=model._dt, fs=True)
+    assert rm.shape_pml == tuple(model.grid.shape)
+    assert np.allclose(rm.damp, model.damp.data, rtol=1e-6, atol=1e-9) and np.array_equal(rm.vp.astype(np.float32), model.vp.data)
+    d64, u64 = ref.forward(rm, src, rec, np.float64(geom.src.data), nt, dt, save=True, space_order=so)
+    e, eu = rel_l2(d.data, d64), rel_l2(u.data, u64)
+    # the surface changes the answer: same run without it is far away
+    model0 = b.Model(origin=(0.,) * nd, spacing=(10.,) * nd, shape=shape, space_order=so, vp=vp, nbl=nbl, bcs="damp")
+    geom0 = b.AcquisitionGeometry(model0, rec, src, 0., 160., f0=0.02, src_type='Ricker')
+    d0, _, _ = b.AcousticWaveSolver(model0, geom0, space_order=so).forward()
+    assert rel_l2(d0.data[:nt], d64) > 0.1
+    residual = b.Receiver(name='res', grid=model.grid, time_range=geom.time_axis, coordinates=rec)
+    residual.data[:] = d64
+    grad, _ = solver.gradient(rec=residual, u=u)
+    g64 = ref.gradient(rm, d64, rec, u64, nt, dt, space_order=so)
+    eg = rel_l2(grad.data, g64)
+    grad_c, _ = solver.gradient(rec=residual, u=None, checkpointing=True, segment=8, keep_segments=1)
+    ec = rel_l2(grad_c.data, g64)
+    print("free surface %d-D so=%d: traces %.2e wavefield %.2e gradient %.2e checkpointed %.2e" % (nd, so, e, eu, eg, ec))
+    assert e <= TOL_TRACE and eu <= TOL_TRACE and eg <= TOL_GRAD and ec <= TOL_GRAD
+    # the adjoint operator takes the same mirrored stencil (iso_stencil(forward=False), operators.py:93-94)
+    srca, _, _ = solver.adjoint(rec=residual)
+    s64 = ref.adjoint(rm, d64, rec, src, nt, dt, space_order=so)
+    s64 = s64[0] if isinstance(s64, tuple) else s64
+    ea = rel_l2(srca.data, s64)
+    print("   adjoint source-side record %.2e" % ea)
+    assert ea <= TOL_TRACE
+
+
+def test_isoacoustic_free_surface_kat_on_gpu():
+    """The reference's own free-surface KAT (acoustic_example.py:75-79: run(fs=True, dtype=float32), |rec|_2 = 369.955,
+    rtol 1e-3) through the product API: demo_model('layers-isotropic', fs=True) + setup_geometry + forward."""
+    b = _b()
+    from devito_fwi_b200.geometry import setup_geometry
+    from devito_fwi_b200.grid import norm
+    shape, spacing = (50, 50, 50), (20., 20., 20.)
+    model = b.demo_model('layers-isotropic', space_order=4, shape=shape, spacing=spacing, nbl=40, dtype=np.float32,
+                         nlayers=3, fs=True)
+    geom = setup_geometry(model, 1000.0)
+    solver = b.AcousticWaveSolver(model, geom, kernel='OT2', space_order=4)
+    rec, _, _ = solver.forward(save=False)
+    n = float(norm(rec))
+    print("free-surface KAT on the GPU: |rec| = %.4f (reference 369.955)" % n)
+    assert np.isclose(n, 369.955, rtol=1e-3, atol=0)
+    # ... and without the surface the reference's other value (459.1678, quoted for float64)
+    model = b.demo_model('layers-isotropic', space_order=4, shape=shape, spacing=spacing, nbl=40, dtype=np.float32, nlayers=3)
+    rec, _, _ = b.AcousticWaveSolver(model, setup_geometry(model, 1000.0), space_order=4).forward(save=False)
+    assert np.isclose(float(norm(rec)), 459.1678, rtol=1e-3, atol=0)

@@ -140,3 +140,34 @@ def test_accuracy_notebook_kat():
     U_t = analytical(30001, time1, time1[1] - time1[0])[0:1501]
     err = np.linalg.norm(U_t[:-1] - d[:-1, 0], 2) / np.sqrt(nt)
     assert np.isclose(err, 1.1265077536675204e-05, rtol=1e-3)      # cell 16 output
+
+
+def test_3d_layers_forward_free_surface_kat():
+    """seismic/acoustic/acoustic_example.py:75-79, fs=True, float32: |rec|_2 = 369.955 (rtol 1e-3) - pins the
+    mirrored top rows (operators.py:8-35) and the one-sided sponge / padding (model.py:33,102-109,157)."""
+    shape, spacing, nbl, so = (50, 50, 50), (20., 20., 20.), 40, 4
+    v = np.empty(shape, dtype=np.float32)
+    v[:] = 1.5
+    vp_i = np.linspace(1.5, 3.5, 3)
+    for i in range(1, 3):
+        v[..., i * int(shape[-1] / 3):] = vp_i[i]
+    norms = {}
+    for dtype in (np.float32, np.float64):
+        model = ref.RefModel((0., 0., 0.), spacing, shape, so, v.astype(dtype), nbl=nbl, dtype=dtype, fs=True)
+        assert model.shape_pml == (130, 130, 90) and float(model.origin_pml[2]) == 0.0
+        assert model.damp[65, 65, 0] == 0 and model.damp[65, 65, -1] > 0 and model.damp[0, 65, 0] > 0
+        dt = float(model.critical_dt)
+        nt, _, tv = ref.time_axis(0., 1000., dt)
+        src = np.array(model.domain_size) * .5
+        src[-1] = 0. + spacing[-1]
+        recx = np.linspace(0., model.domain_size[0], shape[0])
+        recy = np.linspace(0., model.domain_size[1], shape[1])
+        rec = np.empty((shape[0] * shape[1], 3))
+        rec[:, 0] = np.repeat(recx, shape[1])
+        rec[:, 1] = np.tile(recy, shape[0])
+        rec[:, 2] = 2 * spacing[-1]
+        d, _ = ref.forward(model, src, rec, ref.ricker(0.010, tv), nt, dt)
+        norms[dtype] = float(np.linalg.norm(d.astype(np.float64).ravel()))
+    print("free-surface KAT: |rec| fp32 %.4f fp64 %.4f (reference 369.955)" % (norms[np.float32], norms[np.float64]))
+    assert np.isclose(norms[np.float32], 369.955, rtol=1e-3, atol=0)
+    assert np.isclose(norms[np.float64], norms[np.float32], rtol=1e-4)
