@@ -29,7 +29,8 @@ class Grid(ctypes.Structure):
     """struct b2fwi_grid"""
     _fields_ = [("ndim", ctypes.c_int32), ("shape", ctypes.c_int32 * 3),
                 ("space_order", ctypes.c_int32), ("halo", ctypes.c_int32),
-                ("spacing", ctypes.c_float * 3), ("origin", ctypes.c_float * 3), ("fs", ctypes.c_int32)]
+                ("spacing", ctypes.c_float * 3), ("origin", ctypes.c_float * 3), ("fs", ctypes.c_int32),
+                ("kernel", ctypes.c_int32)]
 
 
 class Sparse(ctypes.Structure):

@@ -201,13 +201,18 @@ def checkpointed_gradient(solver, rec, v, grad, vp, dt, checkpoints=None, v_from
     grad_dev = grad._buf.dev(write=True)
     cdt = ctypes.c_float(cw.dt)
 
+    # kernel='OT4': the sweep's own result is not final (the double-Laplacian term is added after it), so the imaging
+    # reads u.dt2 off three slices of the segment's wavefield instead (B2FWI_HIST_U; the buffers hold ta-1 .. tb+1)
+    ot4 = solver.kernel == 'OT4'
+    kind = 1 if ot4 else HIST_UVDT2
+
     def adjoint(ta, tb, hist, t0):
         _lib.check(lib.b2fwi_gradient(
             ctypes.byref(g), _ptr(vp_dev), _ptr(coef), cdt, nt, ta, tb,
-            _ptr(rec_dev), rec_map.byref(), _ptr(hist), HIST_UVDT2, t0, _ptr(v_dev), _ptr(grad_dev), _stream()))
+            _ptr(rec_dev), rec_map.byref(), _ptr(hist), kind, t0, _ptr(v_dev), _ptr(grad_dev), _stream()))
 
     if keepbuf is not None and cw.time_M >= cw.tk:
-        if not v_from_rest:
+        if not v_from_rest and not ot4:
             # grad += -(u[M+1] v[M] - u[M] v[M+1]) / dt^2 ; the m-part is zero: pass 1 starts from a zero ring
             M = cw.time_M
             inv_dt2 = 1.0 / (float(cw.dt) * float(cw.dt))

@@ -52,6 +52,9 @@ int make_layout(const b2fwi_grid *g, Layout *L)
     L->halo = g->halo;
     L->R = R;
     L->fs = g->fs ? 1 : 0;
+    L->ot4 = (g->kernel == 1) ? 1 : 0;
+    B2_CHECK_ARG(g->kernel == 0 || g->kernel == 1, "kernel must be 0 (OT2) or 1 (OT4)");
+    B2_CHECK_ARG(!(L->ot4 && L->fs), "kernel='OT4' with a free surface is not supported");
     if (g->ndim == 2) {
         L->np = 1; L->nr = g->shape[0]; L->nz = g->shape[1];
         L->sr = ((int64_t)L->nz + 2 * H + 31) / 32 * 32;
@@ -91,6 +94,21 @@ void fill_stencil_weights(const Layout &L, StepArgs *a)
     a->c0 = (float)centre;
     a->c0_lo = (float)(centre - (double)a->c0);
 }
+
+// scratch slice for the OT4 correction (stream-ordered allocation, zero in the pitch padding)
+struct Ot4Scratch {
+    float *p = nullptr;
+    cudaStream_t st;
+    int get(const Layout &L, cudaStream_t s)
+    {
+        st = s;
+        if (!L.ot4) return 0;
+        B2_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&p), (size_t)L.elems * sizeof(float), s));
+        B2_CUDA(cudaMemsetAsync(p, 0, (size_t)L.elems * sizeof(float), s));
+        return 0;
+    }
+    ~Ot4Scratch() { if (p) cudaFreeAsync(p, st); }
+};
 
 static int check_time(int nt, int time_m, int time_M)
 {
@@ -176,6 +194,9 @@ int b2fwi_forward(const b2fwi_grid *g, const float *vp, const float *coef, float
     a.box = reinterpret_cast<const int *>(coef + 2 * L.elems);
     a.inv_dt2 = 1.f / (dt * dt);
     a.chunk = pick_chunk(L);
+    Ot4Scratch ot4;
+    if ((rc = ot4.get(L, st))) return rc;
+    B2_CHECK_ARG(!(L.ot4 && d2u_out), "u.dt2 output is not available with kernel='OT4'");
     for (int time = time_m; time <= time_M; time++) {
         const int64_t sn = save ? time + 1 : (time + 1) % 3, sc = save ? time : time % 3,
                       sp = save ? time - 1 : (time - 1) % 3;
@@ -192,6 +213,7 @@ int b2fwi_forward(const b2fwi_grid *g, const float *vp, const float *coef, float
         if (f_inj) { a.inj = *src_map; a.inj_vals = src + (int64_t)time * nsrc; a.vp = vp; a.dt = dt; }
         if (f_itp) { a.itp = *rec_map; a.itp_out = rec + (int64_t)time * nrec; }
         if ((rc = launch_step(L, a, 0, st))) return rc;
+        if (L.ot4 && (rc = launch_ot4_correction(L, a, vp, dt, ot4.p, st))) return rc;
         if (nsrc > 0 && !f_inj &&
             (rc = launch_inject(un, vp, dt, src + (int64_t)time * nsrc, src_map, a.d2u, uc, up, a.inv_dt2, st)))
             return rc;
@@ -223,6 +245,7 @@ static int backward(const b2fwi_grid *g, const float *vp, const float *coef, flo
         B2_CHECK_ARG(hist != nullptr, "hist is NULL");
         B2_CHECK_ARG(hist_kind == B2FWI_HIST_U || hist_kind == B2FWI_HIST_D2U || hist_kind == B2FWI_HIST_UVDT2,
                      "bad hist_kind %d", hist_kind);
+        B2_CHECK_ARG(!(L.ot4 && hist_kind == B2FWI_HIST_UVDT2), "kernel='OT4' images from the saved wavefield (B2FWI_HIST_U)");
         img = (hist_kind == B2FWI_HIST_UVDT2) ? B2FWI_HIST_D2U : hist_kind;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -235,6 +258,8 @@ static int backward(const b2fwi_grid *g, const float *vp, const float *coef, flo
     a.chunk = pick_chunk(L);
     a.grad = grad;
     a.hist_uv = (grad && hist_kind == B2FWI_HIST_UVDT2) ? 1 : 0;
+    Ot4Scratch ot4;
+    if ((rc = ot4.get(L, st))) return rc;
     for (int time = time_M; time >= time_m; time--) {
         float *vn = v + (int64_t)((time - 1) % 3) * L.elems;
         const float *vc = v + (int64_t)(time % 3) * L.elems, *vq = v + (int64_t)((time + 1) % 3) * L.elems;
@@ -252,6 +277,7 @@ static int backward(const b2fwi_grid *g, const float *vp, const float *coef, flo
         if (f_inj) { a.inj = *rec_map; a.inj_vals = rec + (int64_t)time * nrec; a.vp = vp; a.dt = dt; }
         if (f_itp) { a.itp = *src_map; a.itp_out = srca + (int64_t)time * nsrc; }
         if ((rc = launch_step(L, a, img, st))) return rc;
+        if (L.ot4 && (rc = launch_ot4_correction(L, a, vp, dt, ot4.p, st))) return rc;
         if (nrec > 0 && !f_inj &&
             (rc = launch_inject(vn, vp, dt, rec + (int64_t)time * nrec, rec_map, nullptr, nullptr, nullptr, a.inv_dt2, st,
                                 a.hist_uv ? grad : nullptr, a.hist_uv ? a.h1 : nullptr)))
@@ -293,6 +319,7 @@ int b2fwi_born(const b2fwi_grid *g, const float *vp, const float *coef, float dt
     if (rc) return rc;
     if ((rc = check_time(nt, time_m, time_M))) return rc;
     B2_CHECK_ARG(vp && coef && u && U && dm && scratch, "NULL field pointer");
+    B2_CHECK_ARG(!L.ot4, "the Born operator is implemented for kernel='OT2' only");
     const int nsrc = src_map ? src_map->npoint : 0, nrec = rec_map ? rec_map->npoint : 0;
     B2_CHECK_ARG(nsrc == 0 || src, "src is NULL with %d source points", nsrc);
     B2_CHECK_ARG(nrec == 0 || rec, "rec is NULL with %d receiver points", nrec);

@@ -40,6 +40,7 @@ struct Layout {
     int64_t elems;       // floats per haloed slice
     int R;               // stencil radius
     int fs;              // free surface at z index 0 (b2fwi_grid.fs)
+    int ot4;             // fourth-order-in-time update (b2fwi_grid.kernel == 1)
     double inv_h2[3];    // 1/h^2 for plane, row, z directions
 };
 

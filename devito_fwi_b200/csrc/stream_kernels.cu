@@ -578,6 +578,49 @@ int launch_born_source(const Layout &L, float *field, const float *c2, const flo
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// kernel='OT4' (operators.py:38-56): H = L(u) + dt^2/12 * L((1/m) L(u)). The update is linear in H, so a step is the OT2
+// sweep plus  c2 * dt^2/12 * L(vp^2 L(u))  with c2 = dt^2/(m + dt damp): two applications of a plain Laplacian kernel.
+// vp^2 L(u) is taken as zero outside the padded grid (see oracle/fwi_oracle_body.inc: ot4_correction). One point per
+// thread, neighbours through L1/L2: an API-completeness path (the named configurations all run OT2), not a tuned one.
+template <int NDIM>
+__global__ void lap_apply_kernel(const StepArgs a, int R, const float *__restrict__ f, float *__restrict__ out,
+                                 const float *__restrict__ scale, float k, int mode)
+{
+    const int z = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y, p = blockIdx.z;
+    if (z >= a.nz || r >= a.nr) return;
+    const int64_t i = (NDIM == 3 ? (int64_t)p * a.sp : 0) + (int64_t)r * a.sr + z;
+    const float C = f[i];
+    float lap = fmaf(a.c0, C, a.c0_lo * C);
+    for (int d = 1; d <= R; d++) {
+        if (NDIM == 3)
+            lap = fmaf(a.cp[d], (p + d < a.np ? f[i + d * a.sp] : 0.f) + (p - d >= 0 ? f[i - d * a.sp] : 0.f), lap);
+        lap = fmaf(a.cr[d], (r + d < a.nr ? f[i + d * a.sr] : 0.f) + (r - d >= 0 ? f[i - d * a.sr] : 0.f), lap);
+        lap = fmaf(a.cz[d], (z + d < a.nz ? f[i + d] : 0.f) + (z - d >= 0 ? f[i - d] : 0.f), lap);
+    }
+    if (mode == 0) out[i] = scale[i] * scale[i] * lap;            // tmp = vp^2 L(u)
+    else out[i] = fmaf(scale[i] * k, lap, out[i]);                // u+ += c2 dt^2/12 L(tmp)
+}
+
+int launch_ot4_correction(const Layout &L, const StepArgs &a0, const float *vp, float dt, float *tmp, cudaStream_t st)
+{
+    StepArgs a = a0;
+    a.np = L.np; a.nr = L.nr; a.nz = L.nz; a.halo = L.halo; a.sp = L.sp; a.sr = L.sr;
+    if (L.halo != 0 || L.fs) { set_error("OT4 needs halo 0 and no free surface"); return B2FWI_EUNSUPPORTED; }
+    dim3 block(64, 4, 1), grid((L.nz + 63) / 64, (L.nr + 3) / 4, L.ndim == 3 ? L.np : 1);
+    const float k = dt * dt / 12.f;
+    if (L.ndim == 3) {
+        lap_apply_kernel<3><<<grid, block, 0, st>>>(a, L.R, a.cur, tmp, vp, 0.f, 0);
+        lap_apply_kernel<3><<<grid, block, 0, st>>>(a, L.R, tmp, a.out, a.c2, k, 1);
+    } else {
+        lap_apply_kernel<2><<<grid, block, 0, st>>>(a, L.R, a.cur, tmp, vp, 0.f, 0);
+        lap_apply_kernel<2><<<grid, block, 0, st>>>(a, L.R, tmp, a.out, a.c2, k, 1);
+    }
+    B2_CUDA(cudaGetLastError());
+    count_launch(2);
+    return 0;
+}
+
 __global__ void accum_sq_kernel(float *__restrict__ acc, const float *__restrict__ f, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -53,6 +53,8 @@ int launch_inject(float *field, const float *vp, float dt, const float *vals, co
                   float *d2u, const float *cur, const float *prev, float inv_dt2, cudaStream_t st,
                   float *grad = nullptr, const float *hist = nullptr);
 int launch_interp(const float *field, float *out, const b2fwi_sparse *m, cudaStream_t st);
+// kernel='OT4': out += c2 * dt^2/12 * L(vp^2 L(cur)) through the scratch slice `tmp` (two launches)
+int launch_ot4_correction(const Layout &L, const StepArgs &a, const float *vp, float dt, float *tmp, cudaStream_t st);
 int launch_coeffs(const Layout &L, const float *vp, const float *damp, float dt, float *coef, cudaStream_t st);
 int launch_accum_sq(const Layout &L, float *acc, const float *f, cudaStream_t st);
 int launch_born_source(const Layout &L, float *field, const float *c2, const float *dm, const float *d2u,

@@ -43,8 +43,9 @@ class PerformanceSummary(dict):
             self.name, self.time, self.gpointss, self.gbytess)
 
 
-def grid_struct(grid, space_order):
+def grid_struct(grid, space_order, kernel='OT2'):
     g = _lib.Grid()
+    g.kernel = 1 if kernel == 'OT4' else 0
     g.ndim = grid.dim
     g.space_order = int(space_order)
     g.halo = HALO
@@ -85,8 +86,8 @@ class _Timer(object):
 class AcousticWaveSolver(object):
     """Forward / adjoint / gradient operators of the isotropic acoustic wave equation.
 
-    Parameters as in the reference (wavesolver.py:28): ``model``, ``geometry``, ``kernel`` ('OT2'
-    only on this path), ``space_order`` (2..16, even). ``profile=False`` skips the CUDA-event
+    Parameters as in the reference (wavesolver.py:28): ``model``, ``geometry``, ``kernel`` ('OT2', or
+    'OT4' on the streaming engine), ``space_order`` (2..16, even). ``profile=False`` skips the CUDA-event
     timing and its stream synchronisation (summary is then ``None``).
     """
 
@@ -97,8 +98,10 @@ class AcousticWaveSolver(object):
 
         assert self.model.grid == geometry.grid
 
-        if kernel != 'OT2':
-            raise NotImplementedError("kernel %r: only the OT2 scheme is on the B200 hot path" % kernel)
+        if kernel not in ('OT2', 'OT4'):
+            raise ValueError("Unrecognized kernel")          # operators.py:52-53
+        if kernel == 'OT4' and getattr(model, 'fs', False):
+            raise NotImplementedError("kernel='OT4' with a free surface is not implemented")
         if space_order % 2 or not 2 <= space_order <= 16:
             raise ValueError("space_order must be even and in [2, 16]")
         if np.dtype(model.dtype) != np.float32:
@@ -112,11 +115,14 @@ class AcousticWaveSolver(object):
 
     @property
     def dt(self):
+        # Time step can be \sqrt{3}=1.73 bigger with 4th order (wavesolver.py:41-46)
+        if self.kernel == 'OT4':
+            return self.model.dtype(1.73 * self.model.critical_dt)
         return self.model.critical_dt
 
     # ------------------------------------------------------------------ helpers
     def _gs(self):
-        return grid_struct(self.model.grid, self.space_order)
+        return grid_struct(self.model.grid, self.space_order, self.kernel)
 
     def _field_dev(self, f, write=False):
         return f._buf.dev(write=write)

@@ -49,6 +49,10 @@ typedef struct b2fwi_grid {
     float origin[3];       /* padded origin, model.grid.origin (seismic/model.py:100) */
     int32_t fs;            /* free surface at index 0 of the last dimension (Model(fs=True), model.py:102-109): the top
                             * rows take the antisymmetric mirror stencil of operators.py:8-35. Streaming engine only. */
+    int32_t kernel;        /* 0 = 'OT2'; 1 = 'OT4' (operators.py:38-56): every sweep adds the double-Laplacian term
+                            * dt^2/12 * L(vp^2 L(u)) to the update (two more launches per step), the caller passes
+                            * dt = 1.73 x critical_dt (wavesolver.py:41-46). Streaming engine, imaging from the saved
+                            * wavefield (B2FWI_HIST_U) only; not with fs, not for b2fwi_born. */
 } b2fwi_grid;
 
 /*

@@ -50,6 +50,7 @@ typedef struct {
     double spacing[3];
     double origin[3]; /* padded origin (model.py:100), already rounded through the grid dtype */
     int fs;           /* free surface at index 0 of the last dimension (model.py:102-109, operators.py:8-35) */
+    int ot4;          /* kernel='OT4': H = laplace + s^2/12 * biharmonic(1/m) (operators.py:38-56) */
 } oracle_grid;
 
 /*

@@ -29,7 +29,7 @@ _LIBS = {}
 class _Grid(ctypes.Structure):
     _fields_ = [("ndim", ctypes.c_int), ("shape", ctypes.c_int * 3),
                 ("space_order", ctypes.c_int), ("spacing", ctypes.c_double * 3),
-                ("origin", ctypes.c_double * 3), ("fs", ctypes.c_int)]
+                ("origin", ctypes.c_double * 3), ("fs", ctypes.c_int), ("ot4", ctypes.c_int)]
 
 
 def build(fast=False):
@@ -166,6 +166,7 @@ class RefModel(object):
         self.vp = vp.copy() if vp.shape == self.shape_pml else pad_edge(vp, self.nbl, self.fs)
 
     def grid_struct(self, space_order=None):
+        """(set ``self.kernel = 'OT4'`` for the fourth-order-in-time update; the caller passes dt = 1.73 x critical_dt)"""
         g = _Grid()
         g.ndim = self.dim
         g.space_order = int(space_order or self.space_order)
@@ -174,6 +175,7 @@ class RefModel(object):
             g.spacing[d] = self.spacing[d]
             g.origin[d] = float(self.origin_pml[d])
         g.fs = int(self.fs)
+        g.ot4 = int(getattr(self, 'kernel', 'OT2') == 'OT4')
         return g
 
 
