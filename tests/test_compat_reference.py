@@ -10,7 +10,7 @@ REF = "/root/reference"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 COMPAT = os.path.join(ROOT, "devito_fwi_b200", "compat")
 
-pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
 
 
 @pytest.fixture()
@@ -26,6 +26,7 @@ def ref_path(monkeypatch, tmp_path):
             sys.modules.pop(m, None)
 
 
+@needs_ref
 def test_reference_modules_import_on_the_shims(ref_path):
     import fwi
     import minimize          # reference file, does `from fwi import fwi_loss`
@@ -44,6 +45,7 @@ def test_reference_modules_import_on_the_shims(ref_path):
     assert ours._is_l2(misfit.least_square)          # recognised -> on-device misfit
 
 
+@needs_ref
 def test_reference_minimize_runs_unchanged_on_the_fg_contract(ref_path, tmp_path):
     """minimize.py + optimize/NLCG + bracketing line search, unmodified, driven through the
     fwi_loss(x, geometry, obs, misfit, direct_wave, mask, precond[, calc_grad]) -> (f, g float64[n], residuals)
@@ -70,3 +72,28 @@ def test_reference_minimize_runs_unchanged_on_the_fg_contract(ref_path, tmp_path
     assert any(calls) and not all(calls)          # gradient evaluations and forward-only line-search trials
     assert os.path.exists(os.path.join(log, "misfit"))
     assert LazyResidual is not None
+
+
+@pytest.mark.gpu
+def test_reference_optimizer_drives_the_gpu_objective():
+    """minimize.run + optimize.NLCG + misfit.least_square of the reference, unmodified, on the real fwi_loss for two
+    iterations of the circle problem (scripts/run_reference_optimizer.py; a committed run: profiles/r02_reference_optimizer.txt).
+    The reference checkout is not on the GPU box unless B2FWI_REFERENCE points at a copy."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("run_reference_optimizer",
+                                                  os.path.join(ROOT, "scripts", "run_reference_optimizer.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if not os.path.isfile(os.path.join(mod.REF, "minimize.py")):
+        pytest.skip("reference checkout not present")
+    cwd = os.getcwd()
+    try:
+        out = mod.main(2, 3, 'NLCG')
+    finally:
+        os.chdir(cwd)
+        for m in list(sys.modules):
+            if m.split(".")[0] in ("fwi", "seismic", "devito", "w2", "minimize", "optimize", "misfit", "examples"):
+                sys.modules.pop(m, None)
+    h = out["objective_history"]
+    assert len(h) >= 2 and h[-1] < h[0] and out["objective_after"] < h[0]
+    assert out["model_error_after"] < out["model_error_before"] and out["gpu_launches"] > 0
