@@ -63,7 +63,7 @@ def test_resident_engine_vs_oracle(config):
         assert rel_l2(illum[k], il64[nbl:-nbl, nbl:-nbl]) <= TOL_GRAD
         eg = rel_l2(grad[k], g64[nbl:-nbl, nbl:-nbl])
         print("   gradient (own residual) %.2e" % eg)
-        assert eg <= 5 * TOL_GRAD       # includes the amplified trace difference in the residual
+        assert eg <= TOL_GRAD           # (measured 1e-6 .. 6e-6 on all four named configurations)
     # same residual on both sides -> the gradient tolerance proper
     o64, s64, g64, _ = _oracle_shot(g_true, g_init, shots[0])
     res_all = res.clone()
@@ -99,7 +99,7 @@ def test_objective_resident_vs_streaming_vs_oracle():
     print("resident vs host-misfit: f %.2e g %.2e | resident vs streaming: f %.2e g %.2e" % (
         abs(f_r - f_h) / f_h, rel_l2(g_r, g_h), abs(f_r - f_s) / f_s, rel_l2(g_r, g_s)))
     assert abs(f_r - f_h) / f_h < 1e-5 and rel_l2(g_r, g_h) < 1e-6   # host misfit sums in fp32
-    assert abs(f_r - f_s) / f_s < 1e-4 and rel_l2(g_r, g_s) < 2 * TOL_GRAD
+    assert abs(f_r - f_s) / f_s < 1e-5 and rel_l2(g_r, g_s) < TOL_GRAD    # measured 3e-6 / 4e-6
 
     rm_true, rm_init, rm_const = (ref_model(g.model) for g in (g_true, g_init, g_const))
     nt, dt = g_init.nt, float(g_init.dt)
@@ -110,8 +110,8 @@ def test_objective_resident_vs_streaming_vs_oracle():
                                     fw(rm_true), direct_wave=fw(rm_const), mask=mask, precond=True,
                                     calc_grad=True)
     print("resident vs oracle: f %.2e g %.2e" % (abs(f_r - f64) / f64, rel_l2(g_r, g64)))
-    assert abs(f_r - f64) / f64 <= 1e-4
-    assert rel_l2(g_r, g64) <= 5 * TOL_GRAD
+    assert abs(f_r - f64) / f64 <= 1e-5
+    assert rel_l2(g_r, g64) <= TOL_GRAD         # measured 2e-7 / 2e-6
     # forward-only evaluation of the line search
     f2, g2, _ = fwi.fwi_loss(x.ravel(), g_init, obs, fwi.least_square, dw, mask, True, False)
     assert np.isclose(f2, f_r, rtol=1e-9) and not g2.any()
@@ -297,7 +297,7 @@ def test_objective_with_observed_data_on_another_time_axis():
     f2, g2, res2 = fwi.fwi_loss(x, g_init, obs_fine, fwi.least_square, dw, mask, True, True)
     assert len(res2) == 2 and np.asarray(res2[0]).shape == (g_init.nt, 300)
     print("resampled observed data: f %.3e g %.3e" % (abs(f2 - f1) / f1, rel_l2(g2, g1)))
-    assert abs(f2 - f1) <= 1e-4 * f1 and rel_l2(g2, g1) <= 2 * TOL_GRAD
+    assert abs(f2 - f1) <= 1e-5 * f1 and rel_l2(g2, g1) <= TOL_GRAD     # measured 1e-6 / 2e-6
 
 
 def test_residuals_are_snapshots_and_line_search_evaluations_return_fval_only():
