@@ -372,14 +372,24 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
 #pragma unroll
                     for (int k = 1; k <= R; k++) lx = fma4s(a.cx[k], add4(w[(r + R + k) % NW], w[(r + R - k + NW) % NW]), lx);
                     const float zl[12] = {Lq.x, Lq.y, Lq.z, Lq.w, Cq.x, Cq.y, Cq.z, Cq.w, Rq.x, Rq.y, Rq.z, Rq.w};
+                    // odd offsets pair up registers that are not aligned pairs (two MOVs per operand of a packed add):
+                    // their sums are formed by scalar adds straight into an aligned pair instead (same values)
                     const float2 c1k = make_float2(a.cz[1], a.cz[1]);
-                    float2 l01 = __fmul2_rn(c1k, __fadd2_rn(make_float2(zl[5], zl[6]), make_float2(zl[3], zl[4])));
-                    float2 l23 = __fmul2_rn(c1k, __fadd2_rn(make_float2(zl[7], zl[8]), make_float2(zl[5], zl[6])));
+                    float2 l01 = __fmul2_rn(c1k, make_float2(__fadd_rn(zl[5], zl[3]), __fadd_rn(zl[6], zl[4])));
+                    float2 l23 = __fmul2_rn(c1k, make_float2(__fadd_rn(zl[7], zl[5]), __fadd_rn(zl[8], zl[6])));
 #pragma unroll
                     for (int k = 2; k <= R; k++) {
                         const float2 ck = make_float2(a.cz[k], a.cz[k]);
-                        l01 = __ffma2_rn(ck, __fadd2_rn(make_float2(zl[4 + k], zl[5 + k]), make_float2(zl[4 - k], zl[5 - k])), l01);
-                        l23 = __ffma2_rn(ck, __fadd2_rn(make_float2(zl[6 + k], zl[7 + k]), make_float2(zl[6 - k], zl[7 - k])), l23);
+                        float2 s01, s23;
+                        if (k & 1) {
+                            s01 = make_float2(__fadd_rn(zl[4 + k], zl[4 - k]), __fadd_rn(zl[5 + k], zl[5 - k]));
+                            s23 = make_float2(__fadd_rn(zl[6 + k], zl[6 - k]), __fadd_rn(zl[7 + k], zl[7 - k]));
+                        } else {
+                            s01 = __fadd2_rn(make_float2(zl[4 + k], zl[5 + k]), make_float2(zl[4 - k], zl[5 - k]));
+                            s23 = __fadd2_rn(make_float2(zl[6 + k], zl[7 + k]), make_float2(zl[6 - k], zl[7 - k]));
+                        }
+                        l01 = __ffma2_rn(ck, s01, l01);
+                        l23 = __ffma2_rn(ck, s23, l23);
                     }
                     const float4 lap = add4(lx, mk4(l01, l23));
                     // update in increment form
