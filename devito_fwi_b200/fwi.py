@@ -9,6 +9,7 @@ shot loop is partitioned over ranks with one all-reduce of [grad | illum | fval]
 The misfit stays a host plug-in ``misfit_func(syn, obs) -> (fval, adjoint_source)`` on numpy arrays.
 """
 import ctypes
+import warnings
 from copy import deepcopy
 
 import numpy as np
@@ -265,12 +266,33 @@ _SURVEYS = {}
 ENGINE = 'auto'     # 'auto' | 'stream' (force the per-shot streaming engine; used by the parity tests)
 
 
+_FALLBACK_WARNED = set()
+
+
+def _warn_streaming_fallback(geometry):
+    """A 2-D survey the SM-resident engine cannot take (grid beyond 16 SMs' shared memory, space order > 8, free
+    surface, ...) runs shot by shot on the streaming engine, one launch per time step: correct, but an order of
+    magnitude slower per shot on grids this small - say so once per grid instead of dropping there silently."""
+    model = geometry.model
+    if model.grid.dim != 2:
+        return
+    key = (model.grid._key(), model.space_order, bool(getattr(model, 'fs', False)))
+    if key not in _FALLBACK_WARNED:
+        _FALLBACK_WARNED.add(key)
+        warnings.warn("2-D model %s (space_order %d%s) does not fit the SM-resident engine: running shot by shot on the "
+                      "streaming engine (one launch per time step)" % (tuple(model.grid.shape), model.space_order,
+                                                                      ", free surface" if key[2] else ""))
+
+
 def _resident_surveys(geometry, shots):
     """Cached list of ResidentSurvey objects covering ``shots`` in order (one launch group each, see
     resident.partition_shots; a single group whenever all shots fit one wave of clusters), or None when the
     SM-resident engine does not apply."""
     from .resident import ResidentSurvey, partition_shots
-    if ENGINE == 'stream' or not shots or not ResidentSurvey.supported(geometry):
+    if ENGINE == 'stream' or not shots:
+        return None
+    if not ResidentSurvey.supported(geometry):
+        _warn_streaming_fallback(geometry)
         return None
     model = geometry.model
     key = (id(model), model.grid._key(), model.space_order, tuple(shots), float(geometry.dt), geometry.nt,

@@ -23,7 +23,7 @@ for rep in range(2):   # shot 1 pays the one-off allocations (tens of GB of chec
     # residual = the data themselves (any record works for timing; parity is tested at small sizes)
     res._sdata.adopt_dev(rec._sdata.dev().clone())
     torch.cuda.synchronize()
-    grad, s_g = solver.gradient(rec=res, u=cw)           # pass 2: recompute (+u.dt2 store) + adjoint/imaging
+    grad, s_g = solver.gradient(rec=res, u=cw)           # pass 2: recompute + adjoint/imaging (by parts)
     torch.cuda.synchronize()
     if rep == 0:
         first = round(s_f.time + s_g.time, 3)
@@ -34,10 +34,10 @@ out = {"workload": "layered3d %d^3 (+2*%d) so=%d nt=%d, %d receivers" % (n, mode
        "forward": {"s": round(s_f.time, 4), "gpts_per_s": round(s_f.gpointss, 1), "GBs_alg": round(s_f.gbytess, 1),
                    "frac_hbm": round(s_f.gbytess / peak, 3)},
        "gradient_checkpointed": {"s": round(s_g.time, 4),
-                                 "sweeps": "recompute(+u.dt2 store) + adjoint/imaging",
+                                 "sweeps": "recompute + adjoint/imaging (by parts)",
                                  "gpts_per_s_2sweeps": round(2 * npts * steps / s_g.time / 1e9, 1)},
        "shot_gradient_s": round(s_f.time + s_g.time, 3), "first_shot_gradient_s_incl_allocations": first,
-       "shot_gradient": {"sweeps": "forward(+checkpoints) + recompute(+u.dt2 store) + adjoint/imaging",
+       "shot_gradient": {"sweeps": "forward(+checkpoints) + recompute + adjoint/imaging (by parts)",
                          "GBs_alg_52B": round(52.0 * npts * steps / (s_f.time + s_g.time) / 1e9, 1),
                          "frac_hbm_52B": round(52.0 * npts * steps / (s_f.time + s_g.time) / 1e9 / peak, 3),
                          "GBs_moved_76B": round(76.0 * npts * steps / (s_f.time + s_g.time) / 1e9, 1)},
