@@ -43,7 +43,7 @@ struct Scal {            // per-record scalars (device)
 
 struct Ptrs {            // per-call device pointers; record s at offset s * pc (s * mc for the maps)
     float *mu, *nu, *phi, *dual, *rho, *ws, *tmp, *xmap, *ymap, *kern;
-    int *hull;
+    int2 *hull;          // hull stacks of the c-transform lines: (point index, value)
     long long *racc;
     float *freal;        // cuFFT real buffer  [lines][N]
     float2 *fcplx;       // cuFFT complex buffer [lines][N/2+1]
@@ -141,11 +141,37 @@ static __device__ float np_pairwise_sum(const float *v, int64_t n)
     return ret;
 }
 
-__global__ void qw_mass_kernel(const float *__restrict__ f, int64_t pc, int ns, Scal *__restrict__ sc)
+// f.sum() / f.size (misfit.py:73) with numpy's pairwise summation tree, one block per record: the tree splits at
+// n/2 rounded down to a multiple of 8 until a node has <= 128 elements, so its top MASS_DEPTH levels are walked by
+// 2^MASS_DEPTH threads in parallel - each sums its own subtree exactly as numpy would - and the partial sums are
+// combined pairwise in the tree's own order (left + right at every split node).
+#define MASS_DEPTH 8
+#define QW_PF 8              // read-ahead of the hull walk, points
+__global__ void __launch_bounds__(1 << MASS_DEPTH) qw_mass_kernel(const float *__restrict__ f, int64_t pc, int ns,
+                                                                  Scal *__restrict__ sc)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= ns) return;
-    sc[s].mass = __fdiv_rn(np_pairwise_sum(f + (int64_t)s * pc, pc), (float)pc);      // f.sum() / f.size  (misfit.py:73)
+    __shared__ float val[1 << MASS_DEPTH];
+    const int s = blockIdx.x, t = threadIdx.x;
+    const float *v = f + (int64_t)s * pc;
+    int64_t off = 0, len = pc;
+    int leaf_level = MASS_DEPTH;              // level at which this thread's path reaches an unsplit node
+    for (int level = 0; level < MASS_DEPTH; level++) {
+        if (len <= 128) { leaf_level = level; break; }
+        int64_t n2 = len / 2;
+        n2 -= n2 % 8;
+        if ((t >> (MASS_DEPTH - 1 - level)) & 1) { off += n2; len -= n2; }
+        else len = n2;
+    }
+    // an unsplit node above the bottom level is shared by 2^(MASS_DEPTH - leaf_level) threads: the first one sums it
+    const bool owner = (t & ((1 << (MASS_DEPTH - leaf_level)) - 1)) == 0;
+    val[t] = owner ? np_pairwise_sum(v + off, len) : 0.f;
+    __syncthreads();
+    for (int level = MASS_DEPTH - 1; level >= 0; level--) {
+        const int span = 1 << (MASS_DEPTH - level);
+        if ((t & (span - 1)) == 0 && level < leaf_level) val[t] = __fadd_rn(val[t], val[t + span / 2]);
+        __syncthreads();
+    }
+    if (t == 0) sc[s].mass = __fdiv_rn(val[0], (float)pc);
 }
 
 // ------------------------------------------------------------------------------------------------ sequential sums
@@ -177,24 +203,36 @@ static __device__ __forceinline__ float seq_term(const Ptrs &p, int64_t base, in
 }
 
 template <int WHAT>
-__global__ void __launch_bounds__(256) qw_seq_kernel(Ptrs p, int n1, int n2, const float *__restrict__ other)
+__global__ void __launch_bounds__(512) qw_seq_kernel(Ptrs p, int n1, int n2, const float *__restrict__ other)
 {
-    __shared__ float buf[2][SEQ_CHUNK];
+    __shared__ __align__(16) float buf[2][SEQ_CHUNK];
     const int s = blockIdx.x, pc = n1 * n2;
     const int64_t base = (int64_t)s * pc;
     float acc = 0.f;
     const int nchunk = (pc + SEQ_CHUNK - 1) / SEQ_CHUNK;
     for (int i = threadIdx.x; i < SEQ_CHUNK && i < pc; i += blockDim.x) buf[0][i] = seq_term<WHAT>(p, base, i, n1, n2, pc, other);
     __syncthreads();
+    // Warp 0 does nothing but the sequential sum (lane 0; its other lanes idle - in a shared warp the two divergent
+    // paths would take turns at the issue slot and the dependent-add chain, the floor of this kernel at 4 cycles per
+    // element, would wait for the staging code); warps 1.. stage the next chunk meanwhile.
+    const int nstage = (int)blockDim.x - 32;
     for (int c = 0; c < nchunk; c++) {
         const int cnt = min(SEQ_CHUNK, pc - c * SEQ_CHUNK);
         if (threadIdx.x == 0) {
             const float *b = buf[c & 1];
-#pragma unroll 8
-            for (int i = 0; i < cnt; i++) acc = __fadd_rn(acc, b[i]);
-        } else if (c + 1 < nchunk) {
+            const float4 *b4 = reinterpret_cast<const float4 *>(b);
+            int i = 0;
+            for (; i + 16 <= cnt; i += 16) {
+                const float4 v0 = b4[(i >> 2) + 0], v1 = b4[(i >> 2) + 1], v2 = b4[(i >> 2) + 2], v3 = b4[(i >> 2) + 3];
+                acc = __fadd_rn(acc, v0.x); acc = __fadd_rn(acc, v0.y); acc = __fadd_rn(acc, v0.z); acc = __fadd_rn(acc, v0.w);
+                acc = __fadd_rn(acc, v1.x); acc = __fadd_rn(acc, v1.y); acc = __fadd_rn(acc, v1.z); acc = __fadd_rn(acc, v1.w);
+                acc = __fadd_rn(acc, v2.x); acc = __fadd_rn(acc, v2.y); acc = __fadd_rn(acc, v2.z); acc = __fadd_rn(acc, v2.w);
+                acc = __fadd_rn(acc, v3.x); acc = __fadd_rn(acc, v3.y); acc = __fadd_rn(acc, v3.z); acc = __fadd_rn(acc, v3.w);
+            }
+            for (; i < cnt; i++) acc = __fadd_rn(acc, b[i]);
+        } else if (threadIdx.x >= 32 && c + 1 < nchunk) {
             const int i0 = (c + 1) * SEQ_CHUNK;
-            for (int i = threadIdx.x - 1; i < SEQ_CHUNK && i0 + i < pc; i += blockDim.x - 1)
+            for (int i = threadIdx.x - 32; i < SEQ_CHUNK && i0 + i < pc; i += nstage)
                 buf[(c + 1) & 1][i] = seq_term<WHAT>(p, base, i0 + i, n1, n2, pc, other);
         }
         __syncthreads();
@@ -313,58 +351,103 @@ __global__ void qw_set_old_value_kernel(Scal *__restrict__ sc, int ns)
 // One thread per grid line: lower convex hull by the reference's stack walk (fot2d.c:66-104), dual indices by its
 // merge (fot2d.c:106-127) and the dual values with its last-point guard (fot2d.c:129-147). Input element k of line
 // l at in[l * in_line + k * in_elem], negated when `negate` (fot2d.c:167-169); output likewise. The hull stack of
-// a line lives in global memory, entry k of line l at hull[k * nlines_total + l] (coalesced across a warp).
-__global__ void qw_dual_lines_kernel(const float *__restrict__ in, float *__restrict__ out, int *__restrict__ hull,
+// a line lives in global memory, entry k of line l at hull[k * nlines_total + l] (coalesced across a warp), and holds
+// the point's VALUE next to its index; the two entries on top of the stack (hull walk) and the current hull edge
+// (dual walk) are carried in registers. A push is then a store and nothing else, and only a pop (or a step to the
+// next hull edge) reads the stack - one 8-byte load instead of the index -> value chain of dependent loads per point
+// that made the 1501-point column pass 2.8 ms (now the arithmetic of the walk; same operations, same results).
+__global__ void qw_dual_lines_kernel(const float *__restrict__ in, float *__restrict__ out, int2 *__restrict__ hull,
                                      int n, int nlines, int ns, int64_t rec_stride, int in_line, int in_elem, int negate)
 {
+    // slope grid (k + .5) / n as float and the last-point guard sp * (n - .5) / n as double depend on the position
+    // only: tabulated once per block (the walk would otherwise do three double-precision divisions per point)
+    extern __shared__ __align__(8) unsigned char qw_tab[];
+    double *gtab = reinterpret_cast<double *>(qw_tab);              // [n] (double)sp * (n - .5) / (n * 1.0)
+    float *stab = reinterpret_cast<float *>(gtab + n);              // [n] (float)((k + .5) / (n * 1.0))
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const float sp = (float)((k + .5) / (n * 1.0));
+        stab[k] = sp;
+        gtab[k] = (double)sp * (n - .5) / (n * 1.0);
+    }
+    __syncthreads();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = nlines * ns;
     if (t >= total) return;
     const int s = t / nlines, l = t - s * nlines;
     const float *u_ = in + (int64_t)s * rec_stride + (int64_t)l * in_line;
     float *d_ = out + (int64_t)s * rec_stride + (int64_t)l * in_line;
-    int *h = hull + t;
+    int2 *h = hull + t;
     const float sgn = negate ? -1.f : 1.f;
 #define U(k) (sgn * u_[(int64_t)(k)*in_elem])
-#define H(k) h[(int64_t)(k)*total]
-    // get_convex_hull
-    H(0) = 0;
-    H(1) = 1;
+#define HS(k, idx, val) h[(int64_t)(k)*total] = make_int2((idx), __float_as_int(val))
+#define HL(k) h[(int64_t)(k)*total]
+    // get_convex_hull: (ic1, u1) = top of the stack, (ic2, u2) = the entry below it
+    int ic2 = 0, ic1 = 1;
+    float u2 = U(0), u1 = U(1);
+    HS(0, ic2, u2);
+    HS(1, ic1, u1);
     int hc = 2;
-    for (int i = 2; i < n; i++) {
-        const float ui = U(i);
-        for (;;) {
-            if (hc < 2) { H(1) = i; hc++; break; }
-            const int ic1 = H(hc - 1), ic2 = H(hc - 2);
-            const float u1 = U(ic1);
-            const float old_slope = __fdiv_rn(__fsub_rn(u1, U(ic2)), (float)(ic1 - ic2));
-            const float slope = __fdiv_rn(__fsub_rn(ui, u1), (float)(i - ic1));
-            if (slope >= old_slope) { H(hc) = i; hc++; break; }
-            hc--;
+    // the walk itself is a few dozen dependent instructions per point, a global load takes ~1 us: the line is read
+    // QW_PF points ahead (two register chunks), so that the loads of the next chunk fly under the walk of this one
+    float nxt[QW_PF];
+#pragma unroll
+    for (int j = 0; j < QW_PF; j++) nxt[j] = (2 + j < n) ? U(2 + j) : 0.f;
+    for (int i0 = 2; i0 < n; i0 += QW_PF) {
+        float cur[QW_PF];
+#pragma unroll
+        for (int j = 0; j < QW_PF; j++) cur[j] = nxt[j];
+#pragma unroll
+        for (int j = 0; j < QW_PF; j++) nxt[j] = (i0 + QW_PF + j < n) ? U(i0 + QW_PF + j) : 0.f;
+#pragma unroll
+        for (int j = 0; j < QW_PF; j++) {
+            const int i = i0 + j;
+            if (i >= n) break;
+            const float ui = cur[j];
+            for (;;) {
+                if (hc < 2) {                             // only the first point is left: the stack becomes [first, i]
+                    HS(1, i, ui);
+                    hc++;
+                    ic2 = ic1; u2 = u1; ic1 = i; u1 = ui;
+                    break;
+                }
+                const float old_slope = __fdiv_rn(__fsub_rn(u1, u2), (float)(ic1 - ic2));
+                const float slope = __fdiv_rn(__fsub_rn(ui, u1), (float)(i - ic1));
+                if (slope >= old_slope) {
+                    HS(hc, i, ui);
+                    hc++;
+                    ic2 = ic1; u2 = u1; ic1 = i; u1 = ui;
+                    break;
+                }
+                hc--;                                     // pop
+                ic1 = ic2; u1 = u2;
+                if (hc >= 2) { const int2 e = HL(hc - 2); ic2 = e.x; u2 = __int_as_float(e.y); }
+            }
         }
     }
-    // compute_dual_indicies + compute_dual
+    const float ulast = u_[(int64_t)(n - 1) * in_elem] * sgn;
+    // compute_dual_indicies + compute_dual: (ic2, u2) .. (ic1, u1) = the current hull edge, entries counter-1 and counter
     int counter = 1;
-    int ic1 = H(1), ic2 = H(0);
-    float slope = __fdiv_rn(__fmul_rn((float)n, __fsub_rn(U(ic1), U(ic2))), (float)(ic1 - ic2));
-    const float ulast = U(n - 1);
+    { const int2 e0 = HL(0), e1 = HL(1); ic2 = e0.x; u2 = __int_as_float(e0.y); ic1 = e1.x; u1 = __int_as_float(e1.y); }
+    int2 enext = (counter + 1 < hc) ? HL(counter + 1) : make_int2(0, 0);
+    float slope = __fdiv_rn(__fmul_rn((float)n, __fsub_rn(u1, u2)), (float)(ic1 - ic2));
     for (int i = 0; i < n; i++) {
-        const float sp = (float)((i + .5) / (n * 1.0));
+        const float sp = stab[i];
         // (the reference re-evaluates the slope of the current hull edge at the top of every i; same value)
         while (sp > slope && counter < hc - 1) {
             counter++;
-            ic1 = H(counter);
-            ic2 = H(counter - 1);
-            slope = __fdiv_rn(__fmul_rn((float)n, __fsub_rn(U(ic1), U(ic2))), (float)(ic1 - ic2));
+            ic2 = ic1; u2 = u1;
+            ic1 = enext.x; u1 = __int_as_float(enext.y);
+            if (counter + 1 < hc) enext = HL(counter + 1);
+            slope = __fdiv_rn(__fmul_rn((float)n, __fsub_rn(u1, u2)), (float)(ic1 - ic2));
         }
-        const int index = H(counter - 1);
-        const float x = (float)((index + .5) / (n * 1.0));
-        const float v1 = __fsub_rn(__fmul_rn(sp, x), U(index));
-        const float v2 = (float)((double)sp * (n - .5) / (n * 1.0) - (double)ulast);
+        const float x = stab[ic2];                        // ic2 = hull entry counter - 1
+        const float v1 = __fsub_rn(__fmul_rn(sp, x), u2);
+        const float v2 = (float)(gtab[i] - (double)ulast);
         d_[(int64_t)i * in_elem] = (v1 > v2) ? v1 : v2;
     }
 #undef U
-#undef H
+#undef HS
+#undef HL
 }
 
 // ------------------------------------------------------------------------------------------------ push-forward
@@ -659,7 +742,7 @@ static int update_potential(const Ptrs &p, float *pot, const float *other, int n
     qw_poisson_scale_kernel<<<QW_GRID(tot)>>>(p.ws, p.kern, pc, ns);
     if ((rc = dct2d(p, n1, n2, ns, false, st))) return rc;
     qw_axpy_kernel<<<QW_GRID(tot)>>>(pot, p.ws, p.sc, pc, ns);
-    qw_seq_kernel<SEQ_H1><<<ns, 256, 0, st>>>(p, n1, n2, other);
+    qw_seq_kernel<SEQ_H1><<<ns, 512, 0, st>>>(p, n1, n2, other);
     count_launch(4);
     return 0;
 }
@@ -668,8 +751,16 @@ static int update_potential(const Ptrs &p, float *pot, const float *other, int n
 static void dual2d(const Ptrs &p, const float *u, float *dual, int n1, int n2, int ns, cudaStream_t st)
 {
     const int pc = n1 * n2;
-    qw_dual_lines_kernel<<<(unsigned)((n2 * ns + 127) / 128), 128, 0, st>>>(u, p.tmp, p.hull, n1, n2, ns, pc, n1, 1, 0);
-    qw_dual_lines_kernel<<<(unsigned)((n1 * ns + 127) / 128), 128, 0, st>>>(p.tmp, dual, p.hull, n2, n1, ns, pc, 1, n1, 1);
+    // a line is one long dependent chain: with few lines (the column pass: nrec * nshots) one warp per block spreads
+    // them over all SMs instead of four warps on a third of them
+    const int bs1 = (n2 * ns >= 148 * 128) ? 128 : 32, bs2 = (n1 * ns >= 148 * 128) ? 128 : 32;
+    static bool configured = false;          // position tables: 12 B per point of a line (records of up to ~18 k samples)
+    if (!configured) {
+        cudaFuncSetAttribute(qw_dual_lines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        configured = true;
+    }
+    qw_dual_lines_kernel<<<(unsigned)((n2 * ns + bs1 - 1) / bs1), bs1, (size_t)n1 * 12, st>>>(u, p.tmp, p.hull, n1, n2, ns, pc, n1, 1, 0);
+    qw_dual_lines_kernel<<<(unsigned)((n1 * ns + bs2 - 1) / bs2), bs2, (size_t)n2 * 12, st>>>(p.tmp, dual, p.hull, n2, n1, ns, pc, 1, n1, 1);
     count_launch(2);
 }
 
@@ -681,7 +772,7 @@ static void pushforward(const Ptrs &p, const float *pot, const float *dens, int 
     cudaMemsetAsync(p.racc, 0, sizeof(long long) * tot, st);
     qw_splat_kernel<<<QW_GRID(tot)>>>(p, dens, n1, n2, ns);
     qw_fixed_to_float_kernel<<<QW_GRID(tot)>>>(p, tot);
-    qw_seq_kernel<SEQ_RHO><<<ns, 256, 0, st>>>(p, n1, n2, nullptr);
+    qw_seq_kernel<SEQ_RHO><<<ns, 512, 0, st>>>(p, n1, n2, nullptr);
     qw_rho_scale_kernel<<<QW_GRID(tot)>>>(p, pc, ns);
     count_launch(5);
 }
@@ -698,7 +789,7 @@ static Layout2 layout(int n1, int n2, int ns)
     const size_t pc = (size_t)n1 * n2, mc = (size_t)(n1 + 1) * (n2 + 1);
     L.field = align_up(pc * ns * sizeof(float));
     L.maps = align_up(mc * ns * sizeof(float));
-    L.hull = align_up(pc * ns * sizeof(int));
+    L.hull = align_up(pc * ns * sizeof(int2));
     L.racc = align_up(pc * ns * sizeof(long long));
     L.freal = align_up(pc * ns * sizeof(float));
     const size_t c1 = (size_t)(n1 / 2 + 1) * n2, c2 = (size_t)(n2 / 2 + 1) * n1;
@@ -741,7 +832,7 @@ int b2fwi_qw2d_debug_step(int32_t op, int32_t nt, int32_t nrec, float *a, float 
     for (int k = 0; k < 7; k++) { *fields[k] = reinterpret_cast<float *>(b); b += L.field; }
     p.xmap = reinterpret_cast<float *>(b); b += L.maps;
     p.ymap = reinterpret_cast<float *>(b); b += L.maps;
-    p.hull = reinterpret_cast<int *>(b); b += L.hull;
+    p.hull = reinterpret_cast<int2 *>(b); b += L.hull;
     p.racc = reinterpret_cast<long long *>(b); b += L.racc;
     p.freal = reinterpret_cast<float *>(b); b += L.freal;
     p.fcplx = reinterpret_cast<float2 *>(b); b += L.fcplx;
@@ -818,7 +909,7 @@ int b2fwi_qw2d_misfit(const float *syn, const float *obs, const float *dw, int32
     for (int k = 0; k < 7; k++) { *fields[k] = reinterpret_cast<float *>(b); b += L.field; }
     p.xmap = reinterpret_cast<float *>(b); b += L.maps;
     p.ymap = reinterpret_cast<float *>(b); b += L.maps;
-    p.hull = reinterpret_cast<int *>(b); b += L.hull;
+    p.hull = reinterpret_cast<int2 *>(b); b += L.hull;
     p.racc = reinterpret_cast<long long *>(b); b += L.racc;
     p.freal = reinterpret_cast<float *>(b); b += L.freal;
     p.fcplx = reinterpret_cast<float2 *>(b); b += L.fcplx;
@@ -828,13 +919,13 @@ int b2fwi_qw2d_misfit(const float *syn, const float *obs, const float *dw, int32
     // misfit.py:18-45,73 and normalize.c
     qw_min_kernel<<<ns, 256, 0, st>>>(syn, obs, dw, pc, gamma, p.sc);
     qw_shift_kernel<<<QW_GRID(tot)>>>(syn, obs, dw, pc, ns, p.sc, p.mu, p.nu);
-    qw_mass_kernel<<<(ns + 31) / 32, 32, 0, st>>>(p.mu, pc, ns, p.sc);
-    qw_seq_kernel<SEQ_SUM_F><<<ns, 256, 0, st>>>(p, n1, n2, nullptr);
-    qw_seq_kernel<SEQ_SUM_G><<<ns, 256, 0, st>>>(p, n1, n2, nullptr);
+    qw_mass_kernel<<<ns, 1 << MASS_DEPTH, 0, st>>>(p.mu, pc, ns, p.sc);
+    qw_seq_kernel<SEQ_SUM_F><<<ns, 512, 0, st>>>(p, n1, n2, nullptr);
+    qw_seq_kernel<SEQ_SUM_G><<<ns, 512, 0, st>>>(p, n1, n2, nullptr);
     qw_normalize_kernel<<<QW_GRID(tot)>>>(p, n1, n2, ns);
     qw_sigma_kernel<<<ns, 256, 0, st>>>(p, pc, step_scale);
     qw_kernel_kernel<<<QW_GRID(pc)>>>(p.kern, n1, n2);
-    qw_seq_kernel<SEQ_W2><<<ns, 256, 0, st>>>(p, n1, n2, nullptr);          // oldValue (fot2d.c:534)
+    qw_seq_kernel<SEQ_W2><<<ns, 512, 0, st>>>(p, n1, n2, nullptr);          // oldValue (fot2d.c:534)
     qw_set_old_value_kernel<<<(ns + 31) / 32, 32, 0, st>>>(p.sc, ns);
     count_launch(10);
     B2_CUDA(cudaGetLastError());
@@ -844,20 +935,20 @@ int b2fwi_qw2d_misfit(const float *syn, const float *obs, const float *dw, int32
         if ((rc = update_potential(p, p.phi, p.nu, n1, n2, ns, st))) return rc;
         dual2d(p, p.phi, p.dual, n1, n2, ns, st);                           // convexify(phi, dual)
         dual2d(p, p.dual, p.phi, n1, n2, ns, st);
-        qw_seq_kernel<SEQ_W2><<<ns, 256, 0, st>>>(p, n1, n2, nullptr);
+        qw_seq_kernel<SEQ_W2><<<ns, 512, 0, st>>>(p, n1, n2, nullptr);
         qw_step_update_kernel<<<(ns + 31) / 32, 32, 0, st>>>(p.sc, ns);
         pushforward(p, p.phi, p.nu, n1, n2, ns, st);
         if ((rc = update_potential(p, p.dual, p.mu, n1, n2, ns, st))) return rc;
         dual2d(p, p.dual, p.phi, n1, n2, ns, st);                           // convexify(dual, phi)
         dual2d(p, p.phi, p.dual, n1, n2, ns, st);
         pushforward(p, p.dual, p.mu, n1, n2, ns, st);
-        qw_seq_kernel<SEQ_W2><<<ns, 256, 0, st>>>(p, n1, n2, nullptr);
+        qw_seq_kernel<SEQ_W2><<<ns, 512, 0, st>>>(p, n1, n2, nullptr);
         qw_step_update_kernel<<<(ns + 31) / 32, 32, 0, st>>>(p.sc, ns);
         count_launch(4);
         B2_CUDA(cudaGetLastError());
     }
     qw_finish_potentials_kernel<<<QW_GRID(tot)>>>(p, n1, n2, ns);
-    qw_seq_kernel<SEQ_TERM><<<ns, 256, 0, st>>>(p, n1, n2, nullptr);
+    qw_seq_kernel<SEQ_TERM><<<ns, 512, 0, st>>>(p, n1, n2, nullptr);
     qw_adjoint_kernel<<<QW_GRID(tot)>>>(p, adjsrc_out, fval_out, pc, ns);
     qw_loss_kernel<<<1, 32, 0, st>>>(p, ns, fval_out, loss_out);
     count_launch(4);
