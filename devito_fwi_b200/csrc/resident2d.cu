@@ -110,6 +110,19 @@ static __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t 
     } while (!done);
 }
 
+// ---- split step barrier (B2FWI_RES2D_SPLIT_BARRIER, default on)
+// bar.sync at the end of a step made every warp wait for the slowest one with nothing to do. The CTA-wide step barrier is
+// an mbarrier instead: a warp ARRIVES when its rows of u[t+1] are written, then issues what the next step needs from
+// global memory (B / history of its first rows, the gathered injection values, the L2 prefetches), and only WAITS
+// right before it touches the shared tiles again - the load latencies and the warps' skew overlap.
+#ifndef B2FWI_RES2D_SPLIT_BARRIER
+#define B2FWI_RES2D_SPLIT_BARRIER 1
+#endif
+static __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // Hide a value from the optimiser: stops ptxas/nvvm from strength-reducing the per-row addresses of the
 // unrolled row loop into P separately carried registers (which spilled the register-resident state).
 static __device__ __forceinline__ void opaque(uint32_t &x) { asm volatile("" : "+r"(x)); }
@@ -256,14 +269,20 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     uint32_t prv_bar = 0, nex_bar = 0;      // the neighbours' mbarrier pair, through distributed shared memory
     if (crank > 0) prv_bar = mapa_u32(hbar, crank - 1);
     if (crank < a.C - 1) nex_bar = mapa_u32(hbar, crank + 1);
+    const uint32_t sbar = hbar + 16u;         // step barrier (one arrival per warp)
     if (B2FWI_RES2D_ASYNC_HALO && tid == 0) {
         mbar_init(hbar, 1);
         mbar_init(hbar + 8, 1);
+        mbar_init(sbar, (blockDim.x + 31) / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();      // cw_s / cp_s staged
     for (int s = tid; s < ncell; s += blockDim.x) injb[s] = gather(t_first, s);
     cluster.sync();
+#if B2FWI_RES2D_ASYNC_HALO && B2FWI_RES2D_SPLIT_BARRIER
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive_cta(sbar);       // "step -1 is written": the first wait below passes
+#endif
 
     // history pointer of this thread's first row at the first time level; advanced by +-one slice per step
     const int64_t hq = (int64_t)(a.wq1 - a.wq0) * 4;     // history / out row stride (floats)
@@ -321,6 +340,16 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
             }
         }
 
+#if B2FWI_RES2D_ASYNC_HALO && B2FWI_RES2D_SPLIT_BARRIER
+        if (step > 0) {
+            // every warp of this CTA has written its rows of u[t] (and the injection staging), and the neighbours'
+            // boundary rows have landed
+            mbar_wait_cluster(sbar, (uint32_t)step & 1u);
+            mbar_wait_cluster(hbar + 8u * ((step - 1) & 1), (uint32_t)((step - 1) >> 1) & 1u);
+        } else {
+            mbar_wait_cluster(sbar, 0u);
+        }
+#endif
         if (MODE == 0 && a.rec) {
             // rec[t][p] = sum_c w_c u[t][c]   (operators.py:137)
             const int cnt = a.itp_desc[2 * sc], base = a.itp_desc[2 * sc + 1];
@@ -474,7 +503,10 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
             if (stid < ncell) injn[stid] = injv;
             for (int s = stid + blockDim.x; s < ncell; s += blockDim.x) injn[s] = gather(t_next, s);
         }
-#if B2FWI_RES2D_ASYNC_HALO
+#if B2FWI_RES2D_ASYNC_HALO && B2FWI_RES2D_SPLIT_BARRIER
+        __syncwarp();                                                 // this warp's rows of u[t+1] (and its staging) are written
+        if ((tid & 31) == 0) mbar_arrive_cta(sbar);
+#elif B2FWI_RES2D_ASYNC_HALO
         __syncthreads();                                              // this CTA's rows of u[t+1] (and the staging) are written
         mbar_wait_cluster(hbar + 8u * (step & 1), (uint32_t)(step >> 1) & 1u);   // ... and the neighbours' boundary rows have landed
 #else
@@ -488,6 +520,9 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     }
 
 #if B2FWI_RES2D_ASYNC_HALO
+#if B2FWI_RES2D_SPLIT_BARRIER
+    if (nsteps > 0) mbar_wait_cluster(hbar + 8u * ((nsteps - 1) & 1), (uint32_t)((nsteps - 1) >> 1) & 1u);   // last halo bytes
+#endif
     cluster.sync();       // no CTA leaves while a neighbour could still address its shared memory
 #endif
     // ---- window accumulator -> global
@@ -508,7 +543,7 @@ size_t res2d_smem_bytes(const Res2dArgs &a, int P)
     const size_t wcols = (size_t)(a.wq1 - a.wq0) * 4;
     return sizeof(float) * (2 * (size_t)a.tile_rows * pitch + (size_t)a.rows_cta * wcols + (size_t)a.G * P +
                             2 * RES2D_MAX_CELLS + RES2D_MAX_CON) + sizeof(unsigned short) * RES2D_MAX_CON +
-           2 * sizeof(unsigned long long);
+           3 * sizeof(unsigned long long);
 }
 
 template <int R, int P, int MODE>
