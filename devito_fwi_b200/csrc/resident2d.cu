@@ -141,6 +141,9 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
 {
     constexpr int MODE = (MODE_ == 2) ? 0 : MODE_;
     constexpr bool SAVE = (MODE_ == 2);
+    // split step barrier: the backward sweep only (its warps wait 15 % of their time at bar.sync and have the history
+    // loads to overlap; the forward sweeps lose 1 % to the extra instructions)
+    constexpr bool SPLIT = B2FWI_RES2D_ASYNC_HALO && B2FWI_RES2D_SPLIT_BARRIER && (MODE_ == 1);
     extern __shared__ __align__(16) float smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
@@ -279,10 +282,10 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     __syncthreads();      // cw_s / cp_s staged
     for (int s = tid; s < ncell; s += blockDim.x) injb[s] = gather(t_first, s);
     cluster.sync();
-#if B2FWI_RES2D_ASYNC_HALO && B2FWI_RES2D_SPLIT_BARRIER
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive_cta(sbar);       // "step -1 is written": the first wait below passes
-#endif
+    if (SPLIT) {
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive_cta(sbar);   // "step -1 is written": the first wait below passes
+    }
 
     // history pointer of this thread's first row at the first time level; advanced by +-one slice per step
     const int64_t hq = (int64_t)(a.wq1 - a.wq0) * 4;     // history / out row stride (floats)
@@ -340,16 +343,12 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
             }
         }
 
-#if B2FWI_RES2D_ASYNC_HALO && B2FWI_RES2D_SPLIT_BARRIER
-        if (step > 0) {
+        if (SPLIT) {
             // every warp of this CTA has written its rows of u[t] (and the injection staging), and the neighbours'
             // boundary rows have landed
             mbar_wait_cluster(sbar, (uint32_t)step & 1u);
-            mbar_wait_cluster(hbar + 8u * ((step - 1) & 1), (uint32_t)((step - 1) >> 1) & 1u);
-        } else {
-            mbar_wait_cluster(sbar, 0u);
+            if (step > 0) mbar_wait_cluster(hbar + 8u * ((step - 1) & 1), (uint32_t)((step - 1) >> 1) & 1u);
         }
-#endif
         if (MODE == 0 && a.rec) {
             // rec[t][p] = sum_c w_c u[t][c]   (operators.py:137)
             const int cnt = a.itp_desc[2 * sc], base = a.itp_desc[2 * sc + 1];
@@ -503,12 +502,14 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
             if (stid < ncell) injn[stid] = injv;
             for (int s = stid + blockDim.x; s < ncell; s += blockDim.x) injn[s] = gather(t_next, s);
         }
-#if B2FWI_RES2D_ASYNC_HALO && B2FWI_RES2D_SPLIT_BARRIER
-        __syncwarp();                                                 // this warp's rows of u[t+1] (and its staging) are written
-        if ((tid & 31) == 0) mbar_arrive_cta(sbar);
-#elif B2FWI_RES2D_ASYNC_HALO
-        __syncthreads();                                              // this CTA's rows of u[t+1] (and the staging) are written
-        mbar_wait_cluster(hbar + 8u * (step & 1), (uint32_t)(step >> 1) & 1u);   // ... and the neighbours' boundary rows have landed
+#if B2FWI_RES2D_ASYNC_HALO
+        if (SPLIT) {
+            __syncwarp();                                             // this warp's rows of u[t+1] (and its staging) are written
+            if ((tid & 31) == 0) mbar_arrive_cta(sbar);
+        } else {
+            __syncthreads();                                          // this CTA's rows of u[t+1] (and the staging) are written
+            mbar_wait_cluster(hbar + 8u * (step & 1), (uint32_t)(step >> 1) & 1u);   // ... and the neighbours' boundary rows have landed
+        }
 #else
         cluster_barrier();
 #endif
@@ -520,9 +521,8 @@ __global__ void __launch_bounds__(MaxThreads<P>::value, 1) res2d_kernel(const __
     }
 
 #if B2FWI_RES2D_ASYNC_HALO
-#if B2FWI_RES2D_SPLIT_BARRIER
-    if (nsteps > 0) mbar_wait_cluster(hbar + 8u * ((nsteps - 1) & 1), (uint32_t)((nsteps - 1) >> 1) & 1u);   // last halo bytes
-#endif
+    if (SPLIT && nsteps > 0)
+        mbar_wait_cluster(hbar + 8u * ((nsteps - 1) & 1), (uint32_t)((nsteps - 1) >> 1) & 1u);   // last halo bytes
     cluster.sync();       // no CTA leaves while a neighbour could still address its shared memory
 #endif
     // ---- window accumulator -> global
