@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Marmousi L2 FWI on the B200 path, structured like the reference's marmousi_fwi.py:62-181.
+"""Marmousi / Marmousi2 FWI on the B200 path, structured like the reference's marmousi_fwi.py:62-181 and
+marmousi2_fwi.py (L2, 1-D Wasserstein or QW2D misfit).
 
 Observed data from the true model, direct wave from the water model, initial model = smooth_20, bathymetry
 mask, illumination preconditioning, box constraints; the objective is `fwi.fwi_loss` (fwi.py:236-246).
@@ -8,6 +9,7 @@ PYTHONPATH behind `devito_fwi_b200/compat`, otherwise SciPy's L
 reference itself documents at marmousi_fwi.py:165-171).
 
     python examples/marmousi_fwi.py --maxiter 10 --nsrc 29
+    python examples/marmousi_fwi.py --config marmousi2 --misfit qw2d --maxiter 5
     torchrun --nproc-per-node 8 examples/marmousi_fwi.py       # shots sharded over the GPUs
 """
 import argparse
@@ -29,18 +31,29 @@ def main():
     ap.add_argument("--precond", type=int, default=1)
     ap.add_argument("--bathy", type=int, default=1)
     ap.add_argument("--odir", default="./result")
+    ap.add_argument("--config", default="marmousi", choices=["marmousi", "marmousi2"],
+                    help="marmousi_fwi.py (SMARMN, 29 shots) or marmousi2_fwi.py (SMARM2, 31 shots)")
+    ap.add_argument("--misfit", default="l2", choices=["l2", "w1d", "qw2d"],
+                    help="least squares, trace-by-trace 1-D Wasserstein, or the QW2D back-and-forth Wasserstein misfit "
+                         "of marmousi2_fwi.py:131-132 (all three evaluated on the device)")
     args = ap.parse_args()
     import warnings
     warnings.filterwarnings("ignore")
     dist.init_from_env()
     rank0 = dist.rank() == 0
 
-    g_true, g_init, g_const, mask = configs.marmousi(nsrc=args.nsrc)
+    if args.config == "marmousi2":
+        g_true, g_init, g_const, mask = configs.marmousi2(nsrc=args.nsrc if args.nsrc != 29 else 31)
+    else:
+        g_true, g_init, g_const, mask = configs.marmousi(nsrc=args.nsrc)
+    from devito_fwi_b200.misfit import qWasserstein
+    misfit_func = {"l2": fwi.least_square, "w1d": qWasserstein(gamma=1.01, method='1d'),
+                   "qw2d": qWasserstein(gamma=1.01, method='2d', num_steps=15, step_scale=4.)}[args.misfit]
     if not args.bathy:
         mask = None
     obs = fwi.fm_multi(g_true)                      # marmousi_fwi.py:120
     direct_wave = fwi.fm_multi(g_const)             # marmousi_fwi.py:128
-    vmin, vmax = 1.5, 5.2
+    vmin, vmax = (1.5, 5.0) if args.config == "marmousi2" else (1.5, 5.2)      # marmousi2_fwi.py:155-156 / marmousi_fwi.py:154-155
     bounds = [1.0 / vmax ** 2, 1.0 / vmin ** 2]
     shape = g_init.model.shape
     nbl = g_init.model.nbl
@@ -50,7 +63,7 @@ def main():
     history = []
 
     def fun(x):
-        f, g, _ = fwi.fwi_loss(x, g_init, obs, fwi.least_square, direct_wave, mask, bool(args.precond), True)
+        f, g, _ = fwi.fwi_loss(x, g_init, obs, misfit_func, direct_wave, mask, bool(args.precond), True)
         history.append(f)
         return f, g
 
@@ -61,9 +74,9 @@ def main():
         log = os.path.join(args.odir, "log")
         opt = NLCG(ls_method='Bracket', step_len_init=0.05, max_ls=10, log_path=log, verbose=0)
         m = ref_minimize.minimize(opt, maxIter=args.maxiter, ftol=1e-3, gtol=1e-8, log_path=log).run(
-            m0, g_init, obs, fwi.least_square, direct_wave, mask, bool(args.precond), bounds)
+            m0, g_init, obs, misfit_func, direct_wave, mask, bool(args.precond), bounds)
         driver = "reference minimize.py + optimize.NLCG"
-        f_end = fwi.fwi_loss(m, g_init, obs, fwi.least_square, direct_wave, mask, bool(args.precond), False)[0]
+        f_end = fwi.fwi_loss(m, g_init, obs, misfit_func, direct_wave, mask, bool(args.precond), False)[0]
         f_start = None
     except ImportError:
         from scipy.optimize import minimize as sp_minimize
