@@ -133,6 +133,10 @@ int b2fwi_prepare_coeffs(const b2fwi_grid *g, const float *vp, const float *damp
  *                                 rec[time] = interpolate(u[time])
  * u:     save == 0 -> 3 haloed slices, slot = time % 3;  save != 0 -> nt haloed slices (slot = time).
  *        Initial state is read from the caller's u (slots time_m-1, time_m); results are left in place.
+ *        With save != 0 only slots time_m-1 .. time_M+1 are touched, so a window of the history may be passed as
+ *        (buffer - t0 * elems) when buffer[0] holds time level t0: the checkpoint segments of checkpoint.py write
+ *        the wavefield of steps ta..tb straight into an S+2-slice buffer this way, and b2fwi_gradient then images
+ *        from it (hist_t0 = ta - 1).
  * src:   [nt][src_map->npoint] (may be NULL with npoint == 0);  rec: [nt][rec_map->npoint], rows time_m..time_M written.
  * illum: optional haloed slice, incremented by sum_t u[t]^2 over t = time_m .. time_M, plus u[nt-1]^2 when
  *   time_M == nt-2 (the call that produces the last slice adds it): consecutive time windows tile the sum of
