@@ -92,7 +92,9 @@ class CheckpointedWavefield(object):
         return sum(t.numel() * 4 for t in (self.ring, self.ckpt, self.segbuf, self.keepbuf) if t is not None)
 
 
-HBM_FRACTION = 0.85     # share of the free HBM the pass-1 history may take under keep='auto'
+import os
+
+HBM_FRACTION = float(os.environ.get('B2FWI_HBM_FRACTION', 0.85))     # share of the free HBM the pass-1 history may take under keep='auto'
 
 
 def _free_slices(slice_bytes):
